@@ -1,0 +1,95 @@
+/* lungmask_b200 — C ABI of the B200-native lungmask hot path.
+ *
+ * The reference (JoHof/lungmask) is pure Python and has no FFI for this path; the interface each
+ * entry point replaces is therefore a Python function of the reference, cited per function
+ * (paths relative to the reference root).  The Python shell in lungmask_b200/ binds these with
+ * ctypes (INTEGRATION.md shows the stub a maintainer of the reference would add).
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure
+ * (lm_last_error() then returns a static, thread-local message); nothing throws.  The caller owns
+ * all host buffers; the engine owns all device memory.  One engine drives one CUDA device; calls on
+ * one engine must be serialised by the caller.  "dev" variants take device pointers on the engine's
+ * device and run on the engine's stream without host copies.
+ */
+#ifndef LUNGMASK_B200_H
+#define LUNGMASK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lm_engine lm_engine;
+
+#define LM_NET_RES 256           /* mask.py:166: utils.preprocess(..., resolution=[256, 256]) */
+#define LM_MAX_SLOTS 4           /* weight slots (e.g. 0 = base model, 1 = fill model) */
+#define LM_FLAG_NO_POSTPROCESS 1 /* LMInferer(volume_postprocessing=False), mask.py:191-194 */
+
+/* Engine lifetime.  Replaces LMInferer.__init__'s device pick + model.to(device), mask.py:118-139.
+ * batch_capacity = slices per forward wave (the reference's batch_size only bounds memory, results
+ * are per-slice independent; mask.py:172-187). */
+int lm_create(int device, int batch_capacity, lm_engine** out);
+void lm_destroy(lm_engine* e);
+const char* lm_last_error(void);
+int lm_device(const lm_engine* e);
+int lm_batch_capacity(const lm_engine* e);
+
+/* Number of floats lm_load_weights expects for a model with n_classes outputs. */
+size_t lm_weight_blob_floats(int n_classes);
+
+/* Replaces get_model()'s load_state_dict + model.to(device), mask.py:54-68.  `blob` is the live
+ * tensors of the reference state_dict, fp32, concatenated in this order:
+ *   for each of the 18 conv3x3 layers in execution order
+ *     (down_path.{0..4}.block.{0,3}, up_path.{0..3}.conv_block.block.{0,3}):
+ *       conv.weight (OIHW), conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var
+ *   for each up_path.{0..3}.up.1: weight (OI11), bias
+ *   last.weight (K,64,1,1), last.bias (K)
+ * n_classes = len(last.bias) (mask.py:56). */
+int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, int n_classes);
+
+/* LMInferer._inference for numpy input, mask.py:141-210: int16 HU volume (S,H,W) in host memory ->
+ * uint8 label volume (S,H,W) in host memory.  flags: LM_FLAG_*. */
+int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out);
+/* Same with device-resident input and output (no host<->device copies). */
+int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out);
+
+/* LMInferer.apply with a fill model, mask.py:223-232 (two inferences + spare-label fusion +
+ * postprocessing(spare=[max+1]) at the original resolution). */
+int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out);
+
+/* ---- stage-level entry points (each mirrors one reference function; used by the parity tests) ---- */
+
+/* utils.preprocess(img, resolution=[256,256]), utils.py:32-52 (+ simple_bodymask :55-82,
+ * crop_and_resize :85-111): (S,H,W) int16 -> resized (S,256,256) int16 + boxes (S,4) int32
+ * [r0, c0, r1, c1] half-open. */
+int lm_preprocess(lm_engine* e, const int16_t* vol, int S, int H, int W, int16_t* resized, int32_t* boxes);
+/* utils.simple_bodymask, utils.py:55-82: one slice (H,W) int16 (NOT clipped) -> (H,W) uint8 0/1. */
+int lm_simple_bodymask(lm_engine* e, const int16_t* slice, int H, int W, uint8_t* mask);
+
+/* Normalise + UNet.forward + argmax, mask.py:167-187 / resunet.py:58-70: resized (S,256,256) int16 ->
+ * labels (S,256,256) uint8 and, if scores != NULL, the LogSoftmax scores (S,K,256,256) fp32. */
+int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uint8_t* labels, float* scores);
+
+/* utils.postprocessing(label_image, spare, skip_below), utils.py:272-358 on a (S,H,W) uint8 volume. */
+int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
+                   int skip_below, uint8_t* out);
+
+/* [utils.reshape_mask(mask[i], boxes[i], (H,W)) for i], utils.py:114-129 + mask.py:196-202:
+ * (S,256,256) uint8 + boxes -> (S,H,W) uint8. */
+int lm_reshape_masks(lm_engine* e, const uint8_t* masks, const int32_t* boxes, int S, int H, int W, uint8_t* out);
+
+/* Per-stage device time (ms, CUDA events on the engine stream) of the last lm_apply_volume*:
+ * [0] H2D, [1] preprocess, [2] forward, [3] postprocess, [4] reshape, [5] D2H, [6] total.
+ * Also the number of kernels the engine launched in that call. */
+int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launches);
+
+/* Forward-only benchmark hook: runs the forward pass on `S` device-resident resized slices and
+ * reports the device time of the convolution kernels alone (ms) for the roofline. */
+int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* conv_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUNGMASK_B200_H */

@@ -1,0 +1,142 @@
+// CUDA-core kernels around the tensor-core convolutions of the U-Net forward:
+//   * stem_kernel      normalise (mask.py:167-168) + Conv2d(1->64, 3x3, pad 1) + ReLU + BatchNorm
+//                      (resunet.py:93-97 for down_path.0.block.0/2): K = 9, no tensor-core shape.
+//   * upsample2x_kernel  nn.Upsample(mode='bilinear', scale_factor=2) (resunet.py:132), applied AFTER the
+//                      1x1 convolution (the two commute: both are linear and the bilinear weights sum
+//                      to 1), writing the tf32 hi/lo split planes the next convolution consumes.
+//   * prep_conv_weights  OIHW fp32 -> [2][tap][Cout][Cin] tf32 hi/lo planes (one-time, at weight load).
+// All are HBM-bound streaming kernels: 16 threads per pixel x 4 channels each so that every warp store
+// instruction writes two fully coalesced 256-byte runs.
+#include "forward_misc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lm {
+namespace {
+
+__global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
+                                                   const float* __restrict__ w,      // [64][9]
+                                                   const float* __restrict__ bias,   // [64]
+                                                   const float* __restrict__ scale,  // [64]
+                                                   const float* __restrict__ shift,  // [64]
+                                                   int N, int H, int W) {
+  __shared__ float sw[64 * 9], sb[64], ss[64], sh[64];
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) { sb[threadIdx.x] = bias[threadIdx.x]; ss[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
+  __syncthreads();
+  const size_t plane = (size_t)H * W;
+  const size_t total = (size_t)N * plane * 16;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(t & 15);
+    const size_t pix = t >> 4;
+    const int n = (int)(pix / plane);
+    const int r = (int)(pix - (size_t)n * plane);
+    const int y = r / W, x = r - y * W;
+    float v[9];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+      float val = 0.f;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        int hu = in[(size_t)n * plane + (size_t)yy * W + xx];
+        hu = hu > 600 ? 600 : hu;  // mask.py:167 (no-op after the clip in utils.py:45)
+        val = (float)((double)(hu + 1024) / 1624.0);  // mask.py:168 in float64, cast to fp32 at :178-182
+      }
+      v[tap] = val;
+    }
+    float4 hi, lo;
+    float* ph = &hi.x;
+    float* pl = &lo.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = cq * 4 + e;
+      float s = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) s = fmaf(sw[c * 9 + tap], v[tap], s);
+      const float yv = __fadd_rn(__fmul_rn(fmaxf(s + sb[c], 0.f), ss[c]), sh[c]);
+      split_tf32(yv, ph[e], pl[e]);
+    }
+    float* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * 4;
+    *reinterpret_cast<float4*>(o) = hi;
+    *reinterpret_cast<float4*>(o + plane * 64) = lo;
+  }
+}
+
+// in: [N][h][w][C] fp32 -> out: [N][2][2h][2w][C] split planes. PyTorch semantics (align_corners=False):
+// src = max(0.5*(dst+0.5)-0.5, 0), i0 = (int)src, i1 = i0 + (i0 < size-1), l1 = src - i0, l0 = 1 - l1.
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         int N, int h, int w, int C) {
+  const int cq_per_pix = C >> 2;
+  const int H = 2 * h, W = 2 * w;
+  const size_t oplane = (size_t)H * W;
+  const size_t total = (size_t)N * oplane * cq_per_pix;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(t % cq_per_pix);
+    const size_t pix = t / cq_per_pix;
+    const int n = (int)(pix / oplane);
+    const int r = (int)(pix - (size_t)n * oplane);
+    const int y = r / W, x = r - y * W;
+    const float sy = fmaxf(0.5f * ((float)y + 0.5f) - 0.5f, 0.f), sx = fmaxf(0.5f * ((float)x + 0.5f) - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
+    const float* base = in + (size_t)n * h * w * C + cq * 4;
+    const float4 p00 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x0) * C));
+    const float4 p01 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x1) * C));
+    const float4 p10 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x0) * C));
+    const float4 p11 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x1) * C));
+    float4 hi, lo;
+#define LM_BILERP(f)                                                                                     \
+  {                                                                                                      \
+    const float vv = ly0 * (lx0 * p00.f + lx1 * p01.f) + ly1 * (lx0 * p10.f + lx1 * p11.f);              \
+    split_tf32(vv, hi.f, lo.f);                                                                          \
+  }
+    LM_BILERP(x) LM_BILERP(y) LM_BILERP(z) LM_BILERP(w)
+#undef LM_BILERP
+    float* o = out + ((size_t)n * 2 * oplane + r) * C + cq * 4;
+    *reinterpret_cast<float4*>(o) = hi;
+    *reinterpret_cast<float4*>(o + oplane * C) = lo;
+  }
+}
+
+__global__ void prep_conv_weights_kernel(const float* __restrict__ oihw, float* __restrict__ out, int Cout, int Cin,
+                                         int taps) {
+  const size_t total = (size_t)Cout * Cin * taps;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t tap = i % taps, ci = (i / taps) % Cin, co = i / ((size_t)taps * Cin);
+    float hi, lo;
+    split_tf32(oihw[i], hi, lo);
+    const size_t o = (tap * Cout + co) * Cin + ci;
+    out[o] = hi;
+    out[total + o] = lo;
+  }
+}
+
+inline int grid_for(size_t total, int block, int num_sms) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = (size_t)num_sms * 16;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+}  // namespace
+
+int launch_stem(const int16_t* in, float* out, const float* w, const float* bias, const float* scale,
+                const float* shift, int N, int H, int W, int num_sms, cudaStream_t stream) {
+  const size_t total = (size_t)N * H * W * 16;
+  stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, w, bias, scale, shift, N, H, W);
+  return (int)cudaGetLastError();
+}
+
+int launch_upsample2x(const float* in, float* out, int N, int h, int w, int C, int num_sms, cudaStream_t stream) {
+  const size_t total = (size_t)N * 4 * h * w * (C / 4);
+  upsample2x_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, N, h, w, C);
+  return (int)cudaGetLastError();
+}
+
+int launch_prep_conv_weights(const float* oihw, float* out, int Cout, int Cin, int taps, cudaStream_t stream) {
+  const size_t total = (size_t)Cout * Cin * taps;
+  prep_conv_weights_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, stream>>>(
+      oihw, out, Cout, Cin, taps);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace lm
