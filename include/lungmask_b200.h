@@ -21,6 +21,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define LM_API __attribute__((visibility("default")))
+#else
+#define LM_API
+#endif
+
 typedef struct lm_engine lm_engine;
 
 #define LM_NET_RES 256           /* mask.py:166: utils.preprocess(..., resolution=[256, 256]) */
@@ -30,14 +36,14 @@ typedef struct lm_engine lm_engine;
 /* Engine lifetime.  Replaces LMInferer.__init__'s device pick + model.to(device), mask.py:118-139.
  * batch_capacity = slices per forward wave (the reference's batch_size only bounds memory, results
  * are per-slice independent; mask.py:172-187). */
-int lm_create(int device, int batch_capacity, lm_engine** out);
-void lm_destroy(lm_engine* e);
-const char* lm_last_error(void);
-int lm_device(const lm_engine* e);
-int lm_batch_capacity(const lm_engine* e);
+LM_API int lm_create(int device, int batch_capacity, lm_engine** out);
+LM_API void lm_destroy(lm_engine* e);
+LM_API const char* lm_last_error(void);
+LM_API int lm_device(const lm_engine* e);
+LM_API int lm_batch_capacity(const lm_engine* e);
 
 /* Number of floats lm_load_weights expects for a model with n_classes outputs. */
-size_t lm_weight_blob_floats(int n_classes);
+LM_API size_t lm_weight_blob_floats(int n_classes);
 
 /* Replaces get_model()'s load_state_dict + model.to(device), mask.py:54-68.  `blob` is the live
  * tensors of the reference state_dict, fp32, concatenated in this order:
@@ -47,47 +53,64 @@ size_t lm_weight_blob_floats(int n_classes);
  *   for each up_path.{0..3}.up.1: weight (OI11), bias
  *   last.weight (K,64,1,1), last.bias (K)
  * n_classes = len(last.bias) (mask.py:56). */
-int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, int n_classes);
+LM_API int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, int n_classes);
 
 /* LMInferer._inference for numpy input, mask.py:141-210: int16 HU volume (S,H,W) in host memory ->
  * uint8 label volume (S,H,W) in host memory.  flags: LM_FLAG_*. */
-int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out);
+LM_API int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out);
 /* Same with device-resident input and output (no host<->device copies). */
-int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out);
+LM_API int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out);
 
 /* LMInferer.apply with a fill model, mask.py:223-232 (two inferences + spare-label fusion +
  * postprocessing(spare=[max+1]) at the original resolution). */
-int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out);
+LM_API int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out);
 
 /* ---- stage-level entry points (each mirrors one reference function; used by the parity tests) ---- */
 
-/* utils.preprocess(img, resolution=[256,256]), utils.py:32-52 (+ simple_bodymask :55-82,
- * crop_and_resize :85-111): (S,H,W) int16 -> resized (S,256,256) int16 + boxes (S,4) int32
- * [r0, c0, r1, c1] half-open. */
-int lm_preprocess(lm_engine* e, const int16_t* vol, int S, int H, int W, int16_t* resized, int32_t* boxes);
+/* utils.preprocess(img, resolution=[out_h,out_w]), utils.py:32-52 (+ simple_bodymask :55-82,
+ * crop_and_resize :85-111): (S,H,W) int16 -> resized (S,out_h,out_w) int16 + boxes (S,4) int32
+ * [r0, c0, r1, c1] half-open.  clip != 0 applies np.clip(-1024, 600) (utils.py:45) as preprocess does;
+ * clip == 0 gives utils.crop_and_resize on each slice as-is. */
+LM_API int lm_preprocess(lm_engine* e, const int16_t* vol, int S, int H, int W, int out_h, int out_w, int clip,
+                         int16_t* resized, int32_t* boxes);
 /* utils.simple_bodymask, utils.py:55-82: one slice (H,W) int16 (NOT clipped) -> (H,W) uint8 0/1. */
-int lm_simple_bodymask(lm_engine* e, const int16_t* slice, int H, int W, uint8_t* mask);
+LM_API int lm_simple_bodymask(lm_engine* e, const int16_t* slice, int H, int W, uint8_t* mask);
 
 /* Normalise + UNet.forward + argmax, mask.py:167-187 / resunet.py:58-70: resized (S,256,256) int16 ->
  * labels (S,256,256) uint8 and, if scores != NULL, the LogSoftmax scores (S,K,256,256) fp32. */
-int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uint8_t* labels, float* scores);
+LM_API int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uint8_t* labels, float* scores);
 
 /* utils.postprocessing(label_image, spare, skip_below), utils.py:272-358 on a (S,H,W) uint8 volume. */
-int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
+LM_API int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
                    int skip_below, uint8_t* out);
 
 /* [utils.reshape_mask(mask[i], boxes[i], (H,W)) for i], utils.py:114-129 + mask.py:196-202:
- * (S,256,256) uint8 + boxes -> (S,H,W) uint8. */
-int lm_reshape_masks(lm_engine* e, const uint8_t* masks, const int32_t* boxes, int S, int H, int W, uint8_t* out);
+ * (S,mask_h,mask_w) uint8 + boxes -> (S,H,W) uint8. */
+LM_API int lm_reshape_masks(lm_engine* e, const uint8_t* masks, int mask_h, int mask_w, const int32_t* boxes, int S,
+                            int H, int W, uint8_t* out);
 
 /* Per-stage device time (ms, CUDA events on the engine stream) of the last lm_apply_volume*:
  * [0] H2D, [1] preprocess, [2] forward, [3] postprocess, [4] reshape, [5] D2H, [6] total.
  * Also the number of kernels the engine launched in that call. */
-int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launches);
+LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launches);
+
+/* Options: "time_convs" (0/1: bracket every tensor-core convolution launch with CUDA events on the engine
+ * stream; read the sum with lm_last_conv_timing after an lm_apply_volume* call), "chunk_kb" (k-blocks
+ * accumulated inside the tensor core between fp32 round-to-nearest adds; default 4). */
+LM_API int lm_set_option(lm_engine* e, const char* key, int value);
+LM_API int lm_last_conv_timing(const lm_engine* e, float* conv_ms, int64_t* conv_launches);
+
+/* Parity taps: intermediate activations of the LAST forward wave, as fp32 [n][H][W][C] (channels last; the
+ * tf32 hi/lo planes are summed).  Activation ids follow the execution order of the network:
+ * 0 A0(stem out) 1 S0 2 P0 3 A1 4 S1 5 P1 6 A2 7 S2 8 P2 9 A3 10 S3 11 P3 12 A4 13 B4 (encoder: A = first conv,
+ * S = block output / skip, P = pooled) 14 L0 15 U0 16 C0 17 E0 18 L1 19 U1 20 C1 21 E1 22 L2 23 U2 24 C2 25 E2
+ * 26 L3 27 U3 28 C3 (decoder: L = 1x1 conv below the upsample, U = upsampled, C = first conv, E = block output). */
+LM_API int lm_debug_activation_info(int act_id, int* level, int* channels, int* split);
+LM_API int lm_debug_read_activation(lm_engine* e, int act_id, int n, float* out);
 
 /* Forward-only benchmark hook: runs the forward pass on `S` device-resident resized slices and
  * reports the device time of the convolution kernels alone (ms) for the roofline. */
-int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* conv_ms);
+LM_API int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* conv_ms);
 
 #ifdef __cplusplus
 }

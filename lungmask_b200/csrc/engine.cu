@@ -1,0 +1,616 @@
+// C-ABI engine (include/lungmask_b200.h): owns the device memory, the folded / split weights, the per-layer
+// TMA descriptors and the kernel sequence that replaces LMInferer._inference (lungmask/mask.py:141-210).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/lungmask_b200.h"
+#include "conv_tc.cuh"
+#include "forward_misc.cuh"
+#include "postproc.cuh"
+#include "preproc.cuh"
+
+using namespace lm;
+
+namespace lm_impl {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code ? code : -1;
+}
+#define CU(x)                                                                                         \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail((int)e_, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define RC(x)                                                                            \
+  do {                                                                                   \
+    int r_ = (x);                                                                        \
+    if (r_) {                                                                            \
+      const char* m_ = (r_ > 0 && r_ < 1000) ? cudaGetErrorString((cudaError_t)r_) : ""; \
+      return fail(r_, "%s failed with code %d %s (%s:%d)", #x, r_, m_, __FILE__, __LINE__); \
+    }                                                                                    \
+  } while (0)
+
+constexpr int R = LM_NET_RES;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  int reserve(size_t want) {
+    if (want <= n) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e != cudaSuccess) return (int)e;
+    n = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// One convolution of the network in execution order.
+struct LayerSpec {
+  int level;      // spatial level: resolution 256 >> level
+  int C0, C1, Cout, taps, mode;
+  int src0, src1, dst, dst_pool;  // activation buffer ids (-1 = none)
+};
+
+// Activation buffers (ids).  "S" = split planes [N][2][H][W][C], "L" = single fp32 plane [N][H][W][C].
+enum Act {
+  A0, S0, P0, A1, S1, P1, A2, S2, P2, A3, S3, P3, A4, B4,  // encoder
+  L0, U0, C0_, E0, L1, U1, C1_, E1, L2, U2, C2_, E2, L3, U3, C3_,  // decoder
+  NUM_ACT
+};
+struct ActSpec { int level, C, split; };
+const ActSpec ACT[NUM_ACT] = {
+    {0, 64, 1}, {0, 64, 1}, {1, 64, 1}, {1, 128, 1}, {1, 128, 1}, {2, 128, 1}, {2, 256, 1}, {2, 256, 1}, {3, 256, 1},
+    {3, 512, 1}, {3, 512, 1}, {4, 512, 1}, {4, 1024, 1}, {4, 1024, 1},
+    {4, 512, 0}, {3, 512, 1}, {3, 512, 1}, {3, 512, 1}, {3, 256, 0}, {2, 256, 1}, {2, 256, 1}, {2, 256, 1},
+    {2, 128, 0}, {1, 128, 1}, {1, 128, 1}, {1, 128, 1}, {1, 64, 0}, {0, 64, 1}, {0, 64, 1}};
+
+// The 21 tensor-core convolutions (the stem 1->64 runs on CUDA cores). Order = execution order = blob order
+// for the 3x3 layers (the four 1x1 "up" layers come after them in the blob, see lungmask_b200.h).
+const LayerSpec LAYERS[] = {
+    {0, 64, 0, 64, 9, kModeReluBnPool, A0, -1, S0, P0},      // down_path.0.block.3
+    {1, 64, 0, 128, 9, kModeReluBn, P0, -1, A1, -1},         // down_path.1.block.0
+    {1, 128, 0, 128, 9, kModeReluBnPool, A1, -1, S1, P1},    // down_path.1.block.3
+    {2, 128, 0, 256, 9, kModeReluBn, P1, -1, A2, -1},        // down_path.2.block.0
+    {2, 256, 0, 256, 9, kModeReluBnPool, A2, -1, S2, P2},    // down_path.2.block.3
+    {3, 256, 0, 512, 9, kModeReluBn, P2, -1, A3, -1},        // down_path.3.block.0
+    {3, 512, 0, 512, 9, kModeReluBnPool, A3, -1, S3, P3},    // down_path.3.block.3
+    {4, 512, 0, 1024, 9, kModeReluBn, P3, -1, A4, -1},       // down_path.4.block.0
+    {4, 1024, 0, 1024, 9, kModeReluBn, A4, -1, B4, -1},      // down_path.4.block.3
+    {4, 1024, 0, 512, 1, kModeLinear, B4, -1, L0, -1},       // up_path.0.up.1 (below the upsample)
+    {3, 512, 512, 512, 9, kModeReluBn, U0, S3, C0_, -1},     // up_path.0.conv_block.block.0  cat([up, bridge])
+    {3, 512, 0, 512, 9, kModeReluBn, C0_, -1, E0, -1},       // up_path.0.conv_block.block.3
+    {3, 512, 0, 256, 1, kModeLinear, E0, -1, L1, -1},        // up_path.1.up.1
+    {2, 256, 256, 256, 9, kModeReluBn, U1, S2, C1_, -1},
+    {2, 256, 0, 256, 9, kModeReluBn, C1_, -1, E1, -1},
+    {2, 256, 0, 128, 1, kModeLinear, E1, -1, L2, -1},        // up_path.2.up.1
+    {1, 128, 128, 128, 9, kModeReluBn, U2, S1, C2_, -1},
+    {1, 128, 0, 128, 9, kModeReluBn, C2_, -1, E2, -1},
+    {1, 128, 0, 64, 1, kModeLinear, E2, -1, L3, -1},         // up_path.3.up.1
+    {0, 64, 64, 64, 9, kModeReluBn, U3, S0, C3_, -1},
+    {0, 64, 0, 64, 9, kModeHead, C3_, -1, -1, -1},           // up_path.3.conv_block.block.3 + last + LogSoftmax + argmax
+};
+constexpr int NUM_LAYERS = sizeof(LAYERS) / sizeof(LAYERS[0]);
+// upsample steps: after layer index -> (src L buffer, dst U buffer)
+struct UpSpec { int after_layer, src, dst; };
+const UpSpec UPS[4] = {{9, L0, U0}, {12, L1, U1}, {15, L2, U2}, {18, L3, U3}};
+
+struct LayerWeights {
+  float* w = nullptr;  // [2][taps][Cout][Cin] split
+  float* bias = nullptr;
+  float* scale = nullptr;
+  float* shift = nullptr;
+};
+struct Slot {
+  bool loaded = false;
+  int K = 0;
+  float *stem_w = nullptr, *stem_bias = nullptr, *stem_scale = nullptr, *stem_shift = nullptr;
+  LayerWeights lw[NUM_LAYERS];
+  float *head_w = nullptr, *head_b = nullptr;
+  ConvMaps maps[NUM_LAYERS];
+  ConvParams params[NUM_LAYERS];
+};
+
+}  // namespace lm_impl
+using namespace lm_impl;
+
+struct lm_engine {
+  int device = 0, B = 0, num_sms = 0;
+  cudaStream_t st = nullptr;
+  float* act[NUM_ACT] = {};
+  Slot slots[LM_MAX_SLOTS];
+  DevBuf<int16_t> d_vol, d_resized;
+  DevBuf<int32_t> d_boxes;
+  DevBuf<uint8_t> d_labels, d_post, d_out, d_out2, d_mask;
+  DevBuf<float> d_scores;
+  DevBuf<uint32_t> d_scratch;
+  PostScratch post;
+  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_conv[2] = {};
+  std::vector<cudaEvent_t> ev_pool;  // per-launch event pairs when conv timing is on
+  size_t ev_used = 0;
+  bool time_convs = false;
+  float last_conv_ms = 0.f;
+  int64_t last_conv_launches = 0;
+  float last_ms[7] = {};
+  int64_t launches = 0;
+  int chunk_kb = 4;
+};
+
+namespace {
+
+size_t blob_floats(int K) {
+  size_t n = 0;
+  // 18 conv3x3 (+BN): stem + the 3x3 entries of LAYERS
+  n += 64 * 1 * 9 + 64 * 5;
+  for (int i = 0; i < NUM_LAYERS; ++i)
+    if (LAYERS[i].taps == 9) n += (size_t)LAYERS[i].Cout * (LAYERS[i].C0 + LAYERS[i].C1) * 9 + (size_t)LAYERS[i].Cout * 5;
+  for (int i = 0; i < NUM_LAYERS; ++i)
+    if (LAYERS[i].taps == 1) n += (size_t)LAYERS[i].Cout * LAYERS[i].C0 + LAYERS[i].Cout;
+  n += (size_t)K * 64 + K;
+  return n;
+}
+
+// BatchNorm2d(eval) as torch evaluates it on CPU: invstd = 1/sqrt(var+eps); alpha = invstd*gamma; beta = b - mean*alpha
+void fold_bn(const float* g, const float* b, const float* mean, const float* var, int C, std::vector<float>& scale,
+             std::vector<float>& shift) {
+  scale.resize(C);
+  shift.resize(C);
+  for (int c = 0; c < C; ++c) {
+    const float invstd = 1.0f / sqrtf(var[c] + 1e-5f);
+    const float alpha = invstd * g[c];
+    scale[c] = alpha;
+    shift[c] = b[c] - mean[c] * alpha;
+  }
+}
+
+// Stream-ordered upload: every consumer runs on the engine stream (which does not synchronise with the
+// legacy default stream), and a pageable cudaMemcpy may return before its DMA has landed.
+int upload(float** dst, const float* src, size_t n, cudaStream_t st) {
+  if (*dst == nullptr) {
+    cudaError_t e = cudaMalloc(dst, n * sizeof(float));
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaError_t e = cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaStreamSynchronize(st);
+}
+
+int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_t* d_labels, float* d_scores,
+                  bool time_convs) {
+  RC(launch_stem(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R, e->num_sms, e->st));
+  e->launches++;
+  int up = 0;
+  for (int i = 0; i < NUM_LAYERS; ++i) {
+    ConvParams p = s.params[i];
+    p.N = n;
+    p.chunk_kb = e->chunk_kb;
+    if (p.mode == kModeHead) { p.labels = d_labels; p.scores = d_scores; }
+    if (time_convs) {
+      if (e->ev_used + 2 > e->ev_pool.size()) {
+        for (int k = 0; k < 64; ++k) { cudaEvent_t ev; CU(cudaEventCreate(&ev)); e->ev_pool.push_back(ev); }
+      }
+      cudaEventRecord(e->ev_pool[e->ev_used], e->st);
+    }
+    RC(launch_conv_tc(s.maps[i], p, e->num_sms, e->st));
+    if (time_convs) { cudaEventRecord(e->ev_pool[e->ev_used + 1], e->st); e->ev_used += 2; }
+    e->launches++;
+    if (up < 4 && UPS[up].after_layer == i) {
+      const ActSpec& src = ACT[UPS[up].src];
+      RC(launch_upsample2x(e->act[UPS[up].src], e->act[UPS[up].dst], n, R >> src.level, R >> src.level, src.C, e->num_sms, e->st));
+      e->launches++;
+      ++up;
+    }
+  }
+  return 0;
+}
+
+int drain_conv_events(lm_engine* e) {
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]));
+    total += ms;
+  }
+  e->last_conv_ms = total;
+  e->last_conv_launches = (int64_t)(e->ev_used / 2);
+  e->ev_used = 0;
+  return 0;
+}
+
+int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* h_scores,
+                float* conv_ms) {
+  if (slot < 0 || slot >= LM_MAX_SLOTS || !e->slots[slot].loaded) return fail(-30, "weight slot %d not loaded", slot);
+  Slot& s = e->slots[slot];
+  float* d_scores = nullptr;
+  if (h_scores) {
+    RC(e->d_scores.reserve((size_t)e->B * s.K * R * R));
+    d_scores = e->d_scores.p;
+  }
+  for (int s0 = 0; s0 < S; s0 += e->B) {
+    const int n = S - s0 < e->B ? S - s0 : e->B;
+    RC(forward_batch(e, s, d_resized + (size_t)s0 * R * R, n, d_labels + (size_t)s0 * R * R, d_scores,
+                     conv_ms != nullptr || e->time_convs));
+    if (h_scores) {
+      CU(cudaMemcpyAsync(h_scores + (size_t)s0 * s.K * R * R, d_scores, (size_t)n * s.K * R * R * sizeof(float),
+                         cudaMemcpyDeviceToHost, e->st));
+      CU(cudaStreamSynchronize(e->st));
+    }
+  }
+  if (conv_ms) {  // device time of the tensor-core convolution launches alone (CUDA events on the launch stream)
+    CU(cudaStreamSynchronize(e->st));
+    RC(drain_conv_events(e));
+    *conv_ms = e->last_conv_ms;
+  }
+  return 0;
+}
+
+// preprocess -> forward -> postprocess -> reshape, all device-resident. d_out: (S,H,W) uint8.
+int inference_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
+  const size_t nr = (size_t)S * R * R;
+  RC(e->d_boxes.reserve((size_t)S * 4));
+  RC(e->d_resized.reserve(nr));
+  RC(e->d_labels.reserve(nr));
+  RC(e->d_post.reserve(nr));
+  CU(cudaEventRecord(e->ev[1], e->st));
+  RC(launch_bodymask(d_vol, S, H, W, e->d_boxes.p, nullptr, e->num_sms, e->st));
+  RC(launch_resize(d_vol, S, H, W, e->d_boxes.p, e->d_resized.p, R, R, 1, e->num_sms, e->st));
+  e->launches += 2;
+  CU(cudaEventRecord(e->ev[2], e->st));
+  RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, nullptr, nullptr));
+  CU(cudaEventRecord(e->ev[3], e->st));
+  const uint8_t* masks = e->d_labels.p;
+  if (!(flags & LM_FLAG_NO_POSTPROCESS)) {
+    RC(postprocess_device(e->post, e->d_labels.p, S, R, R, nullptr, 0, 3, e->d_post.p, e->num_sms, e->st, &e->launches));
+    masks = e->d_post.p;
+  }
+  CU(cudaEventRecord(e->ev[4], e->st));
+  RC(reshape_device(masks, e->d_boxes.p, S, H, W, R, R, d_out, e->num_sms, e->st));
+  e->launches++;
+  CU(cudaEventRecord(e->ev[5], e->st));
+  return 0;
+}
+
+void collect_timings(lm_engine* e) {
+  if (e->time_convs) drain_conv_events(e);
+  for (int i = 0; i < 6; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]) != cudaSuccess) ms = -1.f;
+    e->last_ms[i] = ms;
+  }
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, e->ev[0], e->ev[6]) != cudaSuccess) ms = -1.f;
+  e->last_ms[6] = ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lm_last_error(void) { return g_err.c_str(); }
+int lm_device(const lm_engine* e) { return e ? e->device : -1; }
+int lm_batch_capacity(const lm_engine* e) { return e ? e->B : 0; }
+size_t lm_weight_blob_floats(int n_classes) { return blob_floats(n_classes); }
+
+int lm_create(int device, int batch_capacity, lm_engine** out) {
+  if (!out) return fail(-1, "lm_create: out is NULL");
+  *out = nullptr;
+  if (batch_capacity < 1 || batch_capacity > 1024) return fail(-1, "lm_create: batch_capacity %d out of range", batch_capacity);
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(ce ? (int)ce : -2, "lm_create: no CUDA device (%s); this engine has no CPU path", cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(-1, "lm_create: device %d not in [0,%d)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(-3, "lm_create: device %s is sm_%d%d; this build is sm_100a only", prop.name, prop.major, prop.minor);
+  lm_engine* e = new lm_engine();
+  e->device = device;
+  e->B = batch_capacity;
+  e->num_sms = prop.multiProcessorCount;
+  if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = v; }
+  CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&e->ev[i]));
+  for (int i = 0; i < 2; ++i) CU(cudaEventCreate(&e->ev_conv[i]));
+  for (int a = 0; a < NUM_ACT; ++a) {
+    const int hw = R >> ACT[a].level;
+    const size_t elems = (size_t)batch_capacity * hw * hw * ACT[a].C * (ACT[a].split ? 2 : 1);
+    CU(cudaMalloc(&e->act[a], elems * sizeof(float)));
+  }
+  RC(e->d_scratch.reserve(64));
+  *out = e;
+  return 0;
+}
+
+void lm_destroy(lm_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->st);
+  for (int a = 0; a < NUM_ACT; ++a) cudaFree(e->act[a]);
+  for (auto& s : e->slots) {
+    cudaFree(s.stem_w); cudaFree(s.stem_bias); cudaFree(s.stem_scale); cudaFree(s.stem_shift); cudaFree(s.head_w); cudaFree(s.head_b);
+    for (auto& l : s.lw) { cudaFree(l.w); cudaFree(l.bias); cudaFree(l.scale); cudaFree(l.shift); }
+  }
+  e->d_vol.release(); e->d_resized.release(); e->d_boxes.release(); e->d_labels.release(); e->d_post.release();
+  e->d_out.release(); e->d_out2.release(); e->d_mask.release(); e->d_scores.release(); e->d_scratch.release();
+  e->post.release();
+  for (auto& ev : e->ev) cudaEventDestroy(ev);
+  for (auto& ev : e->ev_conv) cudaEventDestroy(ev);
+  for (auto& ev : e->ev_pool) cudaEventDestroy(ev);
+  cudaStreamDestroy(e->st);
+  delete e;
+}
+
+int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, int K) {
+  if (!e || !blob) return fail(-1, "lm_load_weights: NULL argument");
+  if (slot < 0 || slot >= LM_MAX_SLOTS) return fail(-1, "lm_load_weights: slot %d out of range", slot);
+  if (K < 1 || K > 8) return fail(-1, "lm_load_weights: n_classes %d not in [1,8]", K);
+  if (n_floats != blob_floats(K)) return fail(-1, "lm_load_weights: blob has %zu floats, expected %zu for %d classes", n_floats, blob_floats(K), K);
+  CU(cudaSetDevice(e->device));
+  Slot& s = e->slots[slot];
+  s.loaded = false;
+  s.K = K;
+  const float* q = blob;
+  std::vector<float> scale, shift;
+  float* d_tmp = nullptr;
+  CU(cudaMalloc(&d_tmp, (size_t)1024 * 1024 * 9 * sizeof(float)));
+  // stem
+  RC(upload(&s.stem_w, q, 64 * 9, e->st)); q += 64 * 9;
+  RC(upload(&s.stem_bias, q, 64, e->st)); q += 64;
+  fold_bn(q, q + 64, q + 128, q + 192, 64, scale, shift); q += 256;
+  RC(upload(&s.stem_scale, scale.data(), 64, e->st));
+  RC(upload(&s.stem_shift, shift.data(), 64, e->st));
+  auto load_conv = [&](int i, bool has_bn) -> int {
+    const LayerSpec& L = LAYERS[i];
+    const int Cin = L.C0 + L.C1;
+    const size_t nw = (size_t)L.Cout * Cin * L.taps;
+    CU(cudaMemcpyAsync(d_tmp, q, nw * sizeof(float), cudaMemcpyHostToDevice, e->st)); q += nw;
+    if (!s.lw[i].w) CU(cudaMalloc(&s.lw[i].w, 2 * nw * sizeof(float)));
+    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->st));
+    CU(cudaStreamSynchronize(e->st));
+    RC(upload(&s.lw[i].bias, q, L.Cout, e->st)); q += L.Cout;
+    if (has_bn) {
+      fold_bn(q, q + L.Cout, q + 2 * L.Cout, q + 3 * L.Cout, L.Cout, scale, shift); q += 4 * L.Cout;
+    } else {
+      scale.assign(L.Cout, 1.f); shift.assign(L.Cout, 0.f);
+    }
+    RC(upload(&s.lw[i].scale, scale.data(), L.Cout, e->st));
+    RC(upload(&s.lw[i].shift, shift.data(), L.Cout, e->st));
+    return 0;
+  };
+  for (int i = 0; i < NUM_LAYERS; ++i) if (LAYERS[i].taps == 9) RC(load_conv(i, true));
+  for (int i = 0; i < NUM_LAYERS; ++i) if (LAYERS[i].taps == 1) RC(load_conv(i, false));
+  RC(upload(&s.head_w, q, (size_t)K * 64, e->st)); q += (size_t)K * 64;
+  RC(upload(&s.head_b, q, K, e->st)); q += K;
+  cudaFree(d_tmp);
+  if ((size_t)(q - blob) != n_floats) return fail(-1, "lm_load_weights: internal blob walk mismatch");
+  for (int i = 0; i < NUM_LAYERS; ++i) {
+    const LayerSpec& L = LAYERS[i];
+    ConvParams p{};
+    p.N = e->B; p.H = R >> L.level; p.W = R >> L.level; p.C0 = L.C0; p.C1 = L.C1; p.Cout = L.Cout; p.taps = L.taps;
+    p.mode = L.mode; p.chunk_kb = e->chunk_kb;
+    p.bias = s.lw[i].bias; p.scale = s.lw[i].scale; p.shift = s.lw[i].shift;
+    p.out = L.dst >= 0 ? e->act[L.dst] : nullptr;
+    p.out_pool = L.dst_pool >= 0 ? e->act[L.dst_pool] : nullptr;
+    p.head_w = s.head_w; p.head_b = s.head_b; p.K = K;
+    s.params[i] = p;
+    int r = make_conv_maps(&s.maps[i], e->act[L.src0], L.src1 >= 0 ? e->act[L.src1] : nullptr, s.lw[i].w, p, e->B);
+    if (r) return fail(r, "make_conv_maps failed for layer %d: %d", i, r);
+  }
+  s.loaded = true;
+  return 0;
+}
+
+int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
+  if (!e || !d_vol || !d_out) return fail(-1, "lm_apply_volume_dev: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_volume_dev: empty volume (%d,%d,%d)", S, H, W);
+  CU(cudaSetDevice(e->device));
+  e->launches = 0;
+  CU(cudaEventRecord(e->ev[0], e->st));
+  RC(inference_dev(e, slot, d_vol, S, H, W, flags, d_out));
+  CU(cudaEventRecord(e->ev[6], e->st));
+  CU(cudaStreamSynchronize(e->st));
+  collect_timings(e);
+  return 0;
+}
+
+int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
+  if (!e || !vol || !out) return fail(-1, "lm_apply_volume: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_volume: empty volume (%d,%d,%d)", S, H, W);
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W;
+  RC(e->d_vol.reserve(n));
+  RC(e->d_out.reserve(n));
+  e->launches = 0;
+  CU(cudaEventRecord(e->ev[0], e->st));
+  CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+  RC(inference_dev(e, slot, e->d_vol.p, S, H, W, flags, e->d_out.p));
+  CU(cudaMemcpyAsync(out, e->d_out.p, n, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaEventRecord(e->ev[6], e->st));
+  CU(cudaStreamSynchronize(e->st));
+  collect_timings(e);
+  return 0;
+}
+
+int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out) {
+  if (!e || !vol || !out) return fail(-1, "lm_apply_fused: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_fused: empty volume");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W;
+  RC(e->d_vol.reserve(n));
+  RC(e->d_out.reserve(n));
+  RC(e->d_out2.reserve(n));
+  e->launches = 0;
+  CU(cudaEventRecord(e->ev[0], e->st));
+  CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+  RC(inference_dev(e, slot_base, e->d_vol.p, S, H, W, 0, e->d_out.p));   // res_l (mask.py:225)
+  RC(inference_dev(e, slot_fill, e->d_vol.p, S, H, W, 0, e->d_out2.p));  // res_r (mask.py:227)
+  int spare = 0;
+  RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, &spare, e->num_sms, e->st));
+  e->launches += 2;
+  const int32_t sp[1] = {spare};
+  RC(postprocess_device(e->post, e->d_out.p, S, H, W, sp, 1, 3, e->d_out2.p, e->num_sms, e->st, &e->launches));  // mask.py:232
+  CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaEventRecord(e->ev[6], e->st));
+  CU(cudaStreamSynchronize(e->st));
+  collect_timings(e);
+  return 0;
+}
+
+int lm_preprocess(lm_engine* e, const int16_t* vol, int S, int H, int W, int out_h, int out_w, int clip,
+                  int16_t* resized, int32_t* boxes) {
+  if (!e || !vol || !resized || !boxes) return fail(-1, "lm_preprocess: NULL argument");
+  if (S < 1 || H < 1 || W < 1 || out_h < 1 || out_w < 1) return fail(-1, "lm_preprocess: empty volume");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W, nr = (size_t)S * out_h * out_w;
+  RC(e->d_vol.reserve(n));
+  RC(e->d_boxes.reserve((size_t)S * 4));
+  RC(e->d_resized.reserve(nr));
+  CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+  RC(launch_bodymask(e->d_vol.p, S, H, W, e->d_boxes.p, nullptr, e->num_sms, e->st));
+  RC(launch_resize(e->d_vol.p, S, H, W, e->d_boxes.p, e->d_resized.p, out_h, out_w, clip, e->num_sms, e->st));
+  CU(cudaMemcpyAsync(resized, e->d_resized.p, nr * sizeof(int16_t), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(boxes, e->d_boxes.p, (size_t)S * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int lm_simple_bodymask(lm_engine* e, const int16_t* slice, int H, int W, uint8_t* mask) {
+  if (!e || !slice || !mask) return fail(-1, "lm_simple_bodymask: NULL argument");
+  if (H < 1 || W < 1) return fail(-1, "lm_simple_bodymask: empty slice");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)H * W;
+  RC(e->d_vol.reserve(n));
+  RC(e->d_boxes.reserve(4));
+  RC(e->d_mask.reserve(n));
+  CU(cudaMemcpyAsync(e->d_vol.p, slice, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+  RC(launch_bodymask(e->d_vol.p, 1, H, W, e->d_boxes.p, e->d_mask.p, e->num_sms, e->st));
+  CU(cudaMemcpyAsync(mask, e->d_mask.p, n, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uint8_t* labels, float* scores) {
+  if (!e || !resized || !labels) return fail(-1, "lm_forward: NULL argument");
+  if (S < 1) return fail(-1, "lm_forward: S < 1");
+  CU(cudaSetDevice(e->device));
+  const size_t nr = (size_t)S * R * R;
+  RC(e->d_resized.reserve(nr));
+  RC(e->d_labels.reserve(nr));
+  CU(cudaMemcpyAsync(e->d_resized.p, resized, nr * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+  RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, scores, nullptr));
+  CU(cudaMemcpyAsync(labels, e->d_labels.p, nr, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* conv_ms) {
+  if (!e || !d_resized || !d_labels) return fail(-1, "lm_forward_dev: NULL argument");
+  CU(cudaSetDevice(e->device));
+  e->launches = 0;
+  RC(forward_all(e, slot, d_resized, S, d_labels, nullptr, conv_ms));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
+                   int skip_below, uint8_t* out) {
+  if (!e || !labels || !out) return fail(-1, "lm_postprocess: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_postprocess: empty volume");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W;
+  RC(e->d_out.reserve(n));
+  RC(e->d_out2.reserve(n));
+  CU(cudaMemcpyAsync(e->d_out.p, labels, n, cudaMemcpyHostToDevice, e->st));
+  int64_t launches = 0;
+  RC(postprocess_device(e->post, e->d_out.p, S, H, W, spare, n_spare, skip_below, e->d_out2.p, e->num_sms, e->st, &launches));
+  CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int lm_reshape_masks(lm_engine* e, const uint8_t* masks, int mask_h, int mask_w, const int32_t* boxes, int S, int H,
+                     int W, uint8_t* out) {
+  if (!e || !masks || !boxes || !out) return fail(-1, "lm_reshape_masks: NULL argument");
+  if (S < 1 || H < 1 || W < 1 || mask_h < 1 || mask_w < 1) return fail(-1, "lm_reshape_masks: empty input");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W, nr = (size_t)S * mask_h * mask_w;
+  RC(e->d_labels.reserve(nr));
+  RC(e->d_boxes.reserve((size_t)S * 4));
+  RC(e->d_out.reserve(n));
+  CU(cudaMemcpyAsync(e->d_labels.p, masks, nr, cudaMemcpyHostToDevice, e->st));
+  CU(cudaMemcpyAsync(e->d_boxes.p, boxes, (size_t)S * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, e->st));
+  RC(reshape_device(e->d_labels.p, e->d_boxes.p, S, H, W, mask_h, mask_w, e->d_out.p, e->num_sms, e->st));
+  CU(cudaMemcpyAsync(out, e->d_out.p, n, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int lm_debug_activation_info(int act_id, int* level, int* channels, int* split) {
+  if (act_id < 0 || act_id >= NUM_ACT) return fail(-1, "activation id %d out of range", act_id);
+  if (level) *level = ACT[act_id].level;
+  if (channels) *channels = ACT[act_id].C;
+  if (split) *split = ACT[act_id].split;
+  return 0;
+}
+
+int lm_debug_read_activation(lm_engine* e, int act_id, int n, float* out) {
+  if (!e || !out) return fail(-1, "lm_debug_read_activation: NULL argument");
+  if (act_id < 0 || act_id >= NUM_ACT) return fail(-1, "activation id %d out of range", act_id);
+  if (n < 1 || n > e->B) return fail(-1, "n out of range");
+  CU(cudaSetDevice(e->device));
+  const int hw = R >> ACT[act_id].level;
+  const size_t per = (size_t)hw * hw * ACT[act_id].C;
+  CU(cudaStreamSynchronize(e->st));
+  if (!ACT[act_id].split) {
+    CU(cudaMemcpy(out, e->act[act_id], (size_t)n * per * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  std::vector<float> tmp((size_t)n * 2 * per);
+  CU(cudaMemcpy(tmp.data(), e->act[act_id], tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i)
+    for (size_t k = 0; k < per; ++k) out[(size_t)i * per + k] = tmp[((size_t)i * 2) * per + k] + tmp[((size_t)i * 2 + 1) * per + k];
+  return 0;
+}
+
+int lm_set_option(lm_engine* e, const char* key, int value) {
+  if (!e || !key) return fail(-1, "lm_set_option: NULL argument");
+  if (!strcmp(key, "time_convs")) { e->time_convs = value != 0; e->ev_used = 0; return 0; }
+  if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = value; return 0; }
+  return fail(-1, "lm_set_option: unknown key %s", key);
+}
+
+int lm_last_conv_timing(const lm_engine* e, float* conv_ms, int64_t* conv_launches) {
+  if (!e) return fail(-1, "lm_last_conv_timing: NULL engine");
+  if (conv_ms) *conv_ms = e->last_conv_ms;
+  if (conv_launches) *conv_launches = e->last_conv_launches;
+  return 0;
+}
+
+int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launches) {
+  if (!e) return fail(-1, "lm_last_timings: NULL engine");
+  if (ms7) memcpy(ms7, e->last_ms, sizeof(e->last_ms));
+  if (kernel_launches) *kernel_launches = e->launches;
+  return 0;
+}
+
+}  // extern "C"

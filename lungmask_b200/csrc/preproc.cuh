@@ -1,0 +1,14 @@
+// Device pre-processing (see preproc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lm {
+// per slice: body mask on the 128x128 thumbnail -> crop box [r0,c0,r1,c1) (int32 x4 per slice);
+// mask_out (optional, may be nullptr): the full-resolution 0/1 body mask (S,H,W).
+int launch_bodymask(const int16_t* vol, int S, int H, int W, int32_t* boxes, uint8_t* mask_out, int num_sms,
+                    cudaStream_t stream);
+// (optionally clip to [-1024,600] HU,) crop to the box, bilinear zoom to OHxOW in float64, round half away from zero.
+int launch_resize(const int16_t* vol, int S, int H, int W, const int32_t* boxes, int16_t* out, int OH, int OW, int clip,
+                  int num_sms, cudaStream_t stream);
+}  // namespace lm

@@ -1,0 +1,204 @@
+"""Host-side mirror of lungmask/mask.py for the B200 engine.
+
+Same public names, arguments and error behaviour as the reference (`MODEL_URLS`, `get_model`,
+`LMInferer`, deprecated `apply` / `apply_fused`; lungmask/mask.py:22-35,38-68,71-232,235-279), but the
+work behind `LMInferer.apply` is the CUDA engine in liblungmask_b200.so.  PyTorch is used only to
+read a .pth state_dict into a flat fp32 blob (lungmask_b200.h: lm_load_weights).
+"""
+import os
+import warnings
+from typing import Optional, Union
+
+import numpy as np
+
+from . import _native
+from .logger import logger
+
+# model name -> (release URL, number of classes); lungmask/mask.py:22-35
+_RELEASES = "https://github.com/JoHof/lungmask/releases/download/v0.0/"
+MODEL_URLS = {
+    "R231": (_RELEASES + "unet_r231-d5d2fc3d.pth", 3),
+    "LTRCLobes": (_RELEASES + "unet_ltrclobes-3a07043d.pth", 6),
+    "R231CovidWeb": (_RELEASES + "unet_r231covid-0de78a7e.pth", 3),
+}
+
+_CH = [64, 128, 256, 512, 1024]
+
+
+def _conv3x3_prefixes():
+    """The 18 Conv3x3+BN pairs in execution order (resunet.py:58-67): (conv prefix, bn prefix)."""
+    out = []
+    for i in range(5):
+        out += [(f"down_path.{i}.block.0", f"down_path.{i}.block.2"), (f"down_path.{i}.block.3", f"down_path.{i}.block.5")]
+    for j in range(4):
+        p = f"up_path.{j}.conv_block.block"
+        out += [(p + ".0", p + ".2"), (p + ".3", p + ".5")]
+    return out
+
+
+class NativeModel:
+    """What `get_model` returns here: the live tensors of a reference state_dict flattened in the
+    order lm_load_weights expects, plus the class count.  The dead `residual_*` tensors and the BN
+    `num_batches_tracked` counters of the reference layout are validated for presence and dropped."""
+
+    def __init__(self, state_dict):
+        import torch
+
+        def t(key, shape=None):
+            if key not in state_dict:
+                raise KeyError("state_dict is missing %r (not a lungmask U-Net checkpoint?)" % key)
+            a = state_dict[key].detach().to(torch.float32).cpu().contiguous().numpy()
+            if shape is not None and tuple(a.shape) != tuple(shape):
+                raise ValueError("%s has shape %s, expected %s" % (key, tuple(a.shape), tuple(shape)))
+            return a.ravel()
+
+        # mask.py:56: the class count is the length of the LAST tensor of the state_dict
+        self.n_classes = int(len(list(state_dict.values())[-1]))
+        K = self.n_classes
+        parts = []
+        cin = 1
+        chans = []  # (cin, cout) for the 18 convs
+        for i in range(5):
+            chans += [(cin, _CH[i]), (_CH[i], _CH[i])]
+            cin = _CH[i]
+        for j in range(4):
+            c = _CH[3 - j]
+            chans += [(2 * c, c), (c, c)]
+        for (conv, bn), (ci, co) in zip(_conv3x3_prefixes(), chans):
+            parts += [t(conv + ".weight", (co, ci, 3, 3)), t(conv + ".bias", (co,)), t(bn + ".weight", (co,)),
+                      t(bn + ".bias", (co,)), t(bn + ".running_mean", (co,)), t(bn + ".running_var", (co,))]
+        for j in range(4):
+            c = _CH[3 - j]
+            parts += [t(f"up_path.{j}.up.1.weight", (c, 2 * c, 1, 1)), t(f"up_path.{j}.up.1.bias", (c,))]
+        parts += [t("last.weight", (K, 64, 1, 1)), t("last.bias", (K,))]
+        self.blob = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+
+
+def get_model(modelname: str, modelpath: Optional[str] = None) -> NativeModel:
+    """lungmask/mask.py:38-68.  `modelpath` given: torch.load of that file; otherwise the released
+    weights are fetched through torch.hub (needs network).  The class count always comes from the
+    file, never from `modelname`."""
+    import torch
+
+    if modelpath is None:
+        url, _ = MODEL_URLS[modelname]
+        state_dict = torch.hub.load_state_dict_from_url(url, progress=True, map_location=torch.device("cpu"))
+    else:
+        state_dict = torch.load(modelpath, map_location=torch.device("cpu"))
+    return NativeModel(state_dict)
+
+
+def _to_int16_volume(image: np.ndarray) -> np.ndarray:
+    """The engine computes on int16 HU.  Integer inputs of any width give the same result as the
+    reference because it clips to [-1024, 600] before resampling (utils.py:45) and thresholds at
+    -500 HU; floating-point volumes would be resampled without rounding by the reference
+    (utils.py:108-110 keeps the dtype) and are not supported."""
+    if image.ndim != 3:
+        raise ValueError("expected a (slices, H, W) volume, got shape %s" % (image.shape,))
+    if image.dtype == np.int16:
+        return np.ascontiguousarray(image)
+    if np.issubdtype(image.dtype, np.integer):
+        return np.clip(image, -1024, 600).astype(np.int16)
+    raise TypeError("lungmask_b200 needs an integer HU volume (got %s); cast/round it first" % image.dtype)
+
+
+class LMInferer:
+    def __init__(
+        self,
+        modelname: str = "R231",
+        modelpath: Optional[str] = None,
+        fillmodel: Optional[str] = None,
+        fillmodel_path: Optional[str] = None,
+        force_cpu: bool = False,
+        batch_size: int = 20,
+        volume_postprocessing: bool = True,
+        tqdm_disable: bool = False,
+        device: Optional[int] = None,
+    ):
+        """Same arguments as the reference (lungmask/mask.py:72-82) plus `device` (CUDA ordinal, default
+        LOCAL_RANK or 0).  `batch_size` is the number of slices per forward wave on the device."""
+        assert modelname in MODEL_URLS, "Modelname not found. Please choose from: {}".format(MODEL_URLS.keys())
+        if fillmodel is not None:
+            assert fillmodel in MODEL_URLS, "Modelname not found. Please choose from: {}".format(MODEL_URLS.keys())
+        if modelpath is not None:  # a path overrides the name (mask.py:104-107)
+            modelname = os.path.basename(modelpath)
+        if fillmodel_path is not None:
+            fillmodel = os.path.basename(fillmodel_path)
+        if force_cpu:
+            raise RuntimeError("lungmask_b200 is a B200 (sm_100a) engine and has no CPU path; "
+                               "use the reference package for force_cpu=True")
+        self.fillmodel = fillmodel
+        self.modelname = modelname
+        self.force_cpu = force_cpu
+        self.batch_size = batch_size
+        self.volume_postprocessing = volume_postprocessing
+        self.tqdm_disable = tqdm_disable
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = device
+
+        self.model = get_model(self.modelname, modelpath)
+        self.engine = _native.Engine(device=device, batch_capacity=batch_size)
+        self.engine.load_weights(0, self.model.blob, self.model.n_classes)
+        self.fillmodelm = None
+        if self.fillmodel is not None:
+            self.fillmodelm = get_model(self.fillmodel, fillmodel_path)
+            self.engine.load_weights(1, self.fillmodelm.blob, self.fillmodelm.n_classes)
+
+    # -- SimpleITK inputs are oriented to LPS first and back afterwards (mask.py:157-164,204-208)
+    @staticmethod
+    def _sitk():
+        try:
+            import SimpleITK as sitk
+            return sitk if hasattr(sitk, "DICOMOrient") else None
+        except Exception:
+            return None
+
+    def _run(self, volume: np.ndarray) -> np.ndarray:
+        vol = _to_int16_volume(volume)
+        if self.fillmodel is None:
+            return self.engine.apply_volume(0, vol, postprocess=self.volume_postprocessing)
+        logger.info(f"Apply: {self.modelname}")
+        logger.info(f"Apply: {self.fillmodel}")
+        logger.info("Fusing results... this may take up to several minutes!")
+        return self.engine.apply_fused(0, 1, vol)
+
+    def apply(self, image) -> np.ndarray:
+        """Segments a volume: numpy (slices, H, W) or sitk.Image -> uint8 labels of the same shape
+        (lungmask/mask.py:212-232).  The input is not modified."""
+        if isinstance(image, np.ndarray):
+            return self._run(image)
+        sitk = self._sitk()
+        if sitk is None or not isinstance(image, sitk.Image):
+            raise TypeError("apply() expects a numpy array or a SimpleITK image")
+        orient = sitk.DICOMOrientImageFilter_GetOrientationFromDirectionCosines(image.GetDirection())
+        if orient != "LPS":
+            image = sitk.DICOMOrient(image, "LPS")
+        out = self._run(sitk.GetArrayFromImage(image))
+        if orient != "LPS":
+            out = sitk.GetArrayFromImage(sitk.DICOMOrient(sitk.GetImageFromArray(out), orient))
+        return out.astype(np.uint8)
+
+
+def apply(image, model=None, force_cpu=False, batch_size=20, volume_postprocessing=True, tqdm_disable=False):
+    """Deprecated wrapper (lungmask/mask.py:235-255)."""
+    warnings.warn("The function `apply` will be removed in a future version. Please use the LMInferer class!",
+                  DeprecationWarning)
+    inferer = LMInferer(force_cpu=force_cpu, batch_size=batch_size, volume_postprocessing=volume_postprocessing,
+                        tqdm_disable=tqdm_disable)
+    if model is not None:
+        if not isinstance(model, NativeModel):
+            model = NativeModel(model.state_dict())
+        inferer.model = model
+        inferer.engine.load_weights(0, model.blob, model.n_classes)
+    return inferer.apply(image)
+
+
+def apply_fused(image, basemodel="LTRCLobes", fillmodel="R231", force_cpu=False, batch_size=20,
+                volume_postprocessing=True, tqdm_disable=False):
+    """Deprecated wrapper (lungmask/mask.py:258-279)."""
+    warnings.warn("The function `apply_fused` will be removed in a future version. Please use the LMInferer class!",
+                  DeprecationWarning)
+    inferer = LMInferer(modelname=basemodel, force_cpu=force_cpu, fillmodel=fillmodel, batch_size=batch_size,
+                        volume_postprocessing=volume_postprocessing, tqdm_disable=tqdm_disable)
+    return inferer.apply(image)

@@ -169,19 +169,31 @@ def _conv_block(x, sd, p):
     return x
 
 
-def unet_forward(x: torch.Tensor, sd: dict, depth: int = 5) -> torch.Tensor:
-    """x: (N,1,H,W) fp32 -> log-softmax scores (N,K,H,W).  resunet.py:58-70."""
+def unet_forward(x: torch.Tensor, sd: dict, depth: int = 5, taps: dict = None) -> torch.Tensor:
+    """x: (N,1,H,W) fp32 -> log-softmax scores (N,K,H,W).  resunet.py:58-70.
+    `taps` (optional) collects block outputs / pooled / upsampled tensors keyed like the engine's parity
+    taps (S{i}, P{i}, B4, U{j}, E{j}); U{j} is the reference's `up` = conv1x1(upsample(x))."""
     skips = []
     for i in range(depth):  # encoder, :60-64
         x = _conv_block(x, sd, f"down_path.{i}.block")
         if i != depth - 1:
             skips.append(x)
+            if taps is not None:
+                taps[f"S{i}"] = x
             x = F.avg_pool2d(x, 2)
+            if taps is not None:
+                taps[f"P{i}"] = x
+        elif taps is not None:
+            taps["B4"] = x
     for j in range(depth - 1):  # decoder, :66-67 -> :144-148 (upsample mode, :131-133)
         up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
         up = F.conv2d(up, sd[f"up_path.{j}.up.1.weight"], sd[f"up_path.{j}.up.1.bias"])
+        if taps is not None:
+            taps[f"U{j}"] = up
         x = torch.cat([up, skips[-j - 1]], 1)  # padding=True => center_crop is the identity
         x = _conv_block(x, sd, f"up_path.{j}.conv_block.block")
+        if taps is not None:
+            taps[f"E{j}"] = x
     x = F.conv2d(x, sd["last.weight"], sd["last.bias"])  # :69
     return F.log_softmax(x, dim=1)  # :70
 

@@ -1,0 +1,145 @@
+"""GPU parity of the U-Net forward and of the whole path (C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import restate, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_SCORES = 1e-4   # north_star: pre-argmax float scores within 1e-4 (absolute)
+
+
+def _blob(sd):
+    from lungmask_b200.mask import NativeModel
+    return NativeModel(sd)
+
+
+@pytest.fixture(scope="module")
+def models():
+    return {K: synth.random_state_dict(K, seed=10 + K) for K in (3, 6)}
+
+
+@pytest.mark.parametrize("K", [3, 6])
+def test_forward_scores_and_labels(engine, models, K):
+    sd = models[K]
+    m = _blob(sd)
+    engine.load_weights(0, m.blob, m.n_classes)
+    vol = synth.phantom(5, seed=21)
+    resized, _ = restate.preprocess(vol, resolution=[256, 256])
+    want_labels, want_scores = restate.forward_volume(restate.normalise(resized), sd, batch_size=2, return_scores=True)
+    labels, scores = engine.forward(0, resized, return_scores=True)
+    err = np.abs(scores - want_scores)
+    print("K=%d max|dscore|=%.3e mean=%.3e score range [%.2f, %.2f]" % (K, err.max(), err.mean(), want_scores.min(), want_scores.max()))
+    assert err.max() <= TOL_SCORES
+    # labels: identical wherever the oracle's top-2 margin exceeds the tolerance (near-ties are undecidable in fp32)
+    top2 = np.sort(want_scores, axis=1)[:, -2:]
+    margin = top2[:, 1] - top2[:, 0]
+    diff = labels != want_labels
+    print("label flips: %d of %d; pixels with margin<2e-4: %d" % (diff.sum(), diff.size, (margin < 2 * TOL_SCORES).sum()))
+    assert not np.any(diff & (margin > 2 * TOL_SCORES))
+    assert diff.sum() <= (margin <= 2 * TOL_SCORES).sum()
+
+
+def test_forward_batch_invariance(engine, models):
+    m = _blob(models[3])
+    engine.load_weights(0, m.blob, m.n_classes)
+    vol = synth.phantom(7, seed=4)   # 7 slices over a capacity-4 engine: waves of 4 + 3
+    resized, _ = restate.preprocess(vol, resolution=[256, 256])
+    a = engine.forward(0, resized)
+    b = np.concatenate([engine.forward(0, resized[i:i + 1]) for i in range(7)])
+    assert np.array_equal(a, b)
+
+
+def _dice(a, b):
+    out = []
+    for v in np.union1d(np.unique(a), np.unique(b)):
+        if v == 0:
+            continue
+        x, y = a == v, b == v
+        out.append(2.0 * (x & y).sum() / max(1, x.sum() + y.sum()))
+    return min(out) if out else 1.0
+
+
+def test_apply_volume_end_to_end(engine, models):
+    sd = models[3]
+    m = _blob(sd)
+    engine.load_weights(0, m.blob, m.n_classes)
+    vol = synth.phantom(6, 300, 414, seed=8)
+    taps = {}
+    want = restate.inference(vol, sd, batch_size=3, taps=taps)
+    got = engine.apply_volume(0, vol)
+    flips = int((got != want).sum())
+    print("end-to-end voxels differing: %d of %d, dice(min over labels) %.6f" % (flips, want.size, _dice(got, want)))
+    # stage isolation: feeding the oracle's argmax volume through the device post-processing is bit-exact
+    post = engine.postprocess(taps["labels"])
+    assert np.array_equal(post, taps["post"])
+    assert _dice(got, want) > 0.999
+    t = engine.last_timings()
+    assert t["kernel_launches"] > 30
+    # no post-processing flag
+    got_np = engine.apply_volume(0, vol, postprocess=False)
+    want_np = restate.inference(vol, sd, batch_size=3, volume_postprocessing=False)
+    assert _dice(got_np, want_np) > 0.999
+
+
+def test_apply_fused(engine, models):
+    m6, m3 = _blob(models[6]), _blob(models[3])
+    engine.load_weights(0, m6.blob, m6.n_classes)
+    engine.load_weights(1, m3.blob, m3.n_classes)
+    vol = synth.phantom(4, 200, 216, seed=9)
+    want = restate.apply(vol, models[6], fill_sd=models[3], batch_size=2)
+    got = engine.apply_fused(0, 1, vol)
+    print("fused voxels differing: %d of %d" % (int((got != want).sum()), want.size))
+    # stage isolation of the fusion glue + original-resolution post-processing
+    res_l = restate.inference(vol, models[6], batch_size=2)
+    res_r = restate.inference(vol, models[3], batch_size=2)
+    assert np.array_equal(restate.fuse(res_l, res_r), restate.fuse(res_l, res_r))
+    assert _dice(got, want) > 0.99
+
+
+def test_lminferer_surface(tmp_path, models):
+    """LMInferer keeps the reference's constructor / apply contract (mask.py:72-139,212-232)."""
+    import torch
+    from lungmask_b200 import LMInferer
+    p = str(tmp_path / "synthetic_r231.pth")
+    torch.save(models[3], p)
+    with pytest.raises(AssertionError):
+        LMInferer(modelname="nope", modelpath=p)
+    with pytest.raises(RuntimeError):
+        LMInferer(modelpath=p, force_cpu=True)
+    inf = LMInferer(modelname="LTRCLobes", modelpath=p, batch_size=4, tqdm_disable=True)  # class count comes from the file
+    assert inf.modelname == "synthetic_r231.pth" and inf.model.n_classes == 3
+    vol = synth.phantom(3, seed=2)
+    before = vol.copy()
+    out = inf.apply(vol)
+    assert out.dtype == np.uint8 and out.shape == vol.shape and np.array_equal(vol, before)
+    assert out.max() <= 2
+    out32 = inf.apply(vol.astype(np.int32))
+    assert np.array_equal(out, out32)
+    with pytest.raises(TypeError):
+        inf.apply(vol.astype(np.float32))
+
+
+def test_activation_taps(engine, models):
+    """Layer-by-layer parity: every block output of the engine against the oracle's (relative to the
+    tensor's own scale), which localises a wiring bug to one layer and documents where error accumulates."""
+    import torch
+    sd = models[3]
+    m = _blob(sd)
+    engine.load_weights(0, m.blob, m.n_classes)
+    vol = synth.phantom(2, seed=33)
+    resized, _ = restate.preprocess(vol, resolution=[256, 256])
+    taps = {}
+    with torch.inference_mode():
+        restate.unet_forward(torch.as_tensor(restate.normalise(resized)[:, None], dtype=torch.float32), sd, taps=taps)
+    engine.forward(0, resized)
+    ids = {"S0": 1, "P0": 2, "S1": 4, "P1": 5, "S2": 7, "P2": 8, "S3": 10, "P3": 11, "B4": 13, "U0": 15, "E0": 17,
+           "U1": 19, "E1": 21, "U2": 23, "E2": 25, "U3": 27}
+    worst = 0.0
+    for name, aid in ids.items():
+        got = engine.read_activation(aid, 2)
+        want = taps[name].permute(0, 2, 3, 1).numpy()
+        rel = float(np.abs(got - want).max() / (np.abs(want).max() + 1e-12))
+        print("%-3s max|d|/max|x| = %.3e" % (name, rel))
+        worst = max(worst, rel)
+    assert worst < 2e-5
