@@ -13,11 +13,14 @@
 //   * B operand: one 4-D TMA box (32 cin, BN cout, 1 tap, 2 planes) per k-block.
 //   * both land 128B-swizzled, K-major, exactly in the canonical tcgen05 shared-memory layout.
 //   * fp32-class accuracy from tf32 tensor cores: operands are pre-split into tf32 hi + tf32 lo planes
-//     and each k-step issues hi*hi, lo*hi, hi*lo (3xTF32). The tensor-core accumulator rounds toward
-//     zero (measured on B200: -6e-5 relative drift over K = 8192, profiles/r01_umma_probe.log), so only
-//     `chunk_kb` k-blocks are accumulated in TMEM; the epilogue warps add each partial tile into fp32
-//     registers with round-to-nearest while the tensor core already works on the next chunk (two TMEM
-//     accumulators, ping-pong).
+//     and each k-step computes hi*hi, hi*lo and lo*hi (3xTF32) with TWO instructions: the B tile's hi and
+//     lo planes are adjacent in shared memory, so  A_hi x [B_hi;B_lo]  is one N = 2*BN MMA whose left half
+//     of the accumulator is hi*hi and whose right half is hi*lo; A_lo x B_hi (N = BN) then adds lo*hi into
+//     that right half. The tensor-core accumulator rounds toward zero (measured on B200: -6e-5 relative
+//     drift over K = 8192, profiles/r01_umma_probe.log), so the dominant hi*hi sum is kept apart from the
+//     2^-11-times-smaller corrections and only `chunk_kb` k-blocks (4 MMA k-steps each) are accumulated in
+//     TMEM; the epilogue warps add each partial tile into fp32 registers with round-to-nearest while the
+//     tensor core already works on the next chunk (two TMEM accumulators of 2*BN columns, ping-pong).
 //   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2
 //     TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, two warps share a quarter and
 //     split the columns).
@@ -40,7 +43,8 @@ struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_PLANE_BYTES + 2 * B_PLANE_BYTES;
   static constexpr int STAGES = (BN == 64) ? 4 : 3;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int ACC_COLS = 2 * BN;       // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;  // two accumulators, ping-pong
   static constexpr int DYN_SMEM = STAGES * STAGE_BYTES + 1024;
 };
 
@@ -127,7 +131,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(BM, BN);
+      const uint32_t idesc_wide = make_idesc_tf32(BM, 2 * BN), idesc_corr = make_idesc_tf32(BM, BN);
       uint32_t gkb = 0, gc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int kb = 0;
@@ -135,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t buf = gc & 1, bph = (gc >> 1) & 1;
           mbar_wait(tempty0 + 8 * buf, bph ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * BN;
+          const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
           const int kend = min(num_kb, kb + chunk_kb);
           uint32_t accum = 0;
           for (; kb < kend; ++kb, ++gkb) {
@@ -145,15 +149,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t a_hi = smem_u32(smem + s * C::STAGE_BYTES);
             const uint64_t d_ahi = make_smem_desc_sw128(a_hi);
             const uint64_t d_alo = make_smem_desc_sw128(a_hi + A_PLANE_BYTES);
-            const uint64_t d_bhi = make_smem_desc_sw128(a_hi + 2 * A_PLANE_BYTES);
-            const uint64_t d_blo = make_smem_desc_sw128(a_hi + 2 * A_PLANE_BYTES + C::B_PLANE_BYTES);
+            const uint64_t d_b = make_smem_desc_sw128(a_hi + 2 * A_PLANE_BYTES);  // B_hi rows, B_lo rows follow
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const uint64_t ko = (uint64_t)(k * 2);  // 8 tf32 = 32 B along K, >>4
-              umma_tf32(d_tmem, d_ahi + ko, d_bhi + ko, idesc, accum);
+              umma_tf32(d_tmem, d_ahi + ko, d_b + ko, idesc_wide, accum);    // [hi*hi | hi*lo]
               accum = 1;
-              umma_tf32(d_tmem, d_alo + ko, d_bhi + ko, idesc, 1);
-              umma_tf32(d_tmem, d_ahi + ko, d_blo + ko, idesc, 1);
+              umma_tf32(d_tmem + BN, d_alo + ko, d_b + ko, idesc_corr, 1);   // += lo*hi into the right half
             }
             umma_commit(empty0 + 8 * s);
           }
@@ -179,11 +181,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < NC / 32; ++j) {
-          float v[32];
-          tmem_ld32(tmem_base + lane_base + buf * BN + half * NC + j * 32, v);
+          float v[32], w[32];
+          const uint32_t col = buf * C::ACC_COLS + half * NC + j * 32;
+          tmem_ld32(tmem_base + lane_base + col, v);        // hi*hi partial sums
+          tmem_ld32(tmem_base + lane_base + col + BN, w);   // hi*lo + lo*hi corrections
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
+          for (int i = 0; i < 32; ++i) acc[j * 32 + i] = (acc[j * 32 + i] + v[i]) + w[i];
         }
         tc_fence_before();
         __syncwarp();

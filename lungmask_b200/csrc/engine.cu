@@ -152,7 +152,7 @@ struct lm_engine {
   int64_t last_conv_launches = 0;
   float last_ms[7] = {};
   int64_t launches = 0;
-  int chunk_kb = 4;
+  int chunk_kb = 1;
 };
 
 namespace {
@@ -399,6 +399,8 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   };
   for (int i = 0; i < NUM_LAYERS; ++i) if (LAYERS[i].taps == 9) RC(load_conv(i, true));
   for (int i = 0; i < NUM_LAYERS; ++i) if (LAYERS[i].taps == 1) RC(load_conv(i, false));
+  cudaFree(s.head_w); cudaFree(s.head_b);  // sized by the class count of the previous load
+  s.head_w = s.head_b = nullptr;
   RC(upload(&s.head_w, q, (size_t)K * 64, e->st)); q += (size_t)K * 64;
   RC(upload(&s.head_b, q, K, e->st)); q += K;
   cudaFree(d_tmp);
@@ -595,6 +597,7 @@ int lm_debug_read_activation(lm_engine* e, int act_id, int n, float* out) {
 int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!e || !key) return fail(-1, "lm_set_option: NULL argument");
   if (!strcmp(key, "time_convs")) { e->time_convs = value != 0; e->ev_used = 0; return 0; }
+  if (!strcmp(key, "post_debug_stage")) { e->post.debug_stage = value; return 0; }
   if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = value; return 0; }
   return fail(-1, "lm_set_option: unknown key %s", key);
 }

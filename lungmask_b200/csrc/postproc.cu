@@ -101,12 +101,19 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __r
   }
 }
 
+// Read-only walk: while flattening, a thread may only write its OWN slot; a path-halving write from another
+// walker could overwrite an already flattened slot with a stale non-root ancestor.
+__device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t i) {
+  uint32_t p = parent[i];
+  while (p != i) { i = p; p = parent[i]; }
+  return i;
+}
 __global__ void ccl_flatten_kernel(uint32_t* __restrict__ parent, Dim d, Box b) {
   const size_t n = box_volume(b);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
     const uint32_t i = box_voxel(b, d, t, z, y, x);
-    if (parent[i] != NONE) parent[i] = uf_find(parent, i);
+    if (parent[i] != NONE) parent[i] = uf_find_ro(parent, i);
   }
 }
 
@@ -345,6 +352,15 @@ __global__ void map_labels_kernel(const uint32_t* __restrict__ rid, uint32_t* __
     }
     mapped[i] = v;
     if (!present[v]) present[v] = 1;
+  }
+}
+
+__global__ void debug_ids_kernel(const uint32_t* __restrict__ rid, uint32_t* __restrict__ cur, uint8_t* __restrict__ out,
+                                 size_t n, int merged) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t o = rid[i];
+    if (o && merged) o = cur_find(cur, o);
+    out[i] = (uint8_t)(o & 255u);
   }
 }
 
@@ -622,6 +638,12 @@ int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, i
     LM_CUDA(cudaStreamSynchronize(st));
   }
 
+  if (ws.debug_stage == 1) { LM_CUDA(cudaMemcpyAsync(d_out, ws.mapped, n, cudaMemcpyDeviceToDevice, st)); return 0; }
+  if (ws.debug_stage == 2 || ws.debug_stage == 3) {
+    if (R) debug_ids_kernel<<<g, 256, 0, st>>>(ws.rid, ws.r_cur, d_out, n, ws.debug_stage == 3);
+    else LM_CUDA(cudaMemsetAsync(d_out, 0, n, st));
+    return (int)cudaGetLastError();
+  }
   // Q6
   LM_CUDA(cudaMemsetAsync(d_out, 0, n, st));
   rc = run_ccl<26>(ws.mapped, ws.parent, d, full, num_sms, st, launches);

@@ -244,7 +244,7 @@ def keep_largest_connected_component(mask: np.ndarray) -> np.ndarray:
     return lab == (np.argsort(areas)[-1] + 1)
 
 
-def postprocessing(label_image: np.ndarray, spare=(), skip_below: int = 3) -> np.ndarray:
+def postprocessing(label_image: np.ndarray, spare=(), skip_below: int = 3, taps: dict = None) -> np.ndarray:
     """utils.py:272-358.
 
     1. 26-connected components of equal label value (ids in raster order)            :293
@@ -264,6 +264,8 @@ def postprocessing(label_image: np.ndarray, spare=(), skip_below: int = 3) -> np
     """
     spare = list(spare)
     regionmask = cc_label(label_image)
+    if taps is not None:
+        taps["regions0"] = regionmask.copy()
     origlabels = np.unique(label_image)
     record = np.zeros((max(origlabels) + 1,), dtype=np.uint32)
     regions = regionprops(regionmask, label_image)
@@ -298,6 +300,9 @@ def postprocessing(label_image: np.ndarray, spare=(), skip_below: int = 3) -> np
 
     mapped = to_label[regionmask]
     mapped[np.isin(mapped, spare)] = 0
+    if taps is not None:
+        taps["regions1"] = regionmask.copy()
+        taps["mapped"] = mapped.copy()
 
     if mapped.shape[0] == 1:
         def fill(x):

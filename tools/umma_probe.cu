@@ -135,6 +135,57 @@ probe_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, 2 * BN); }
 }
 
+
+// T6: can a SW128 K-major A operand start at an arbitrary 128-byte row of a larger TMA-written tile and use
+// an 8-row-group stride (SBO) other than 1024 B?  (Needed to slice the 9 shifted 3x3-tap views out of ONE
+// halo patch in shared memory instead of loading the activation tile nine times.)
+__global__ void __launch_bounds__(128, 1)
+probe_rowoffset(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                float* __restrict__ D, int row0, int sbo_rows, int a_rows, int base_offset_mode) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t full = smem_u32(&bars[0]), done = smem_u32(&bars[1]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int BN = 64;
+  const int a_bytes = a_rows * 128;
+  const int a_bytes_al = (a_bytes + 1023) & ~1023;
+  if (threadIdx.x == 0) { mbar_init(full, 1); mbar_init(done, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 64);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(full, a_bytes + BN * 128);
+    tma_load_2d(smem_u32(smem), &tmA, full, 0, 0);
+    tma_load_2d(smem_u32(smem) + a_bytes_al, &tmB, full, 0, 0);
+    mbar_wait(full, 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(smem) + row0 * 128;
+    uint64_t adesc = 0;
+    adesc |= (uint64_t)((a_addr & 0x3FFFF) >> 4);
+    adesc |= (uint64_t)1 << 16;
+    adesc |= (uint64_t)((sbo_rows * 128) >> 4) << 32;
+    adesc |= (uint64_t)1 << 46;
+    if (base_offset_mode) adesc |= (uint64_t)((a_addr >> 7) & 7) << 49;
+    adesc |= (uint64_t)2 << 61;
+    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem) + a_bytes_al);
+    const uint32_t idesc = make_idesc_tf32(128, BN);
+    for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k ? 1u : 0u);
+    umma_commit(done);
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  float v[32];
+  for (int j = 0; j < 2; ++j) {
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 32, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) D[(size_t)(warp * 32 + lane) * BN + j * 32 + i] = v[i];
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -223,9 +274,46 @@ static void test_exact() {
   }
 }
 
+
+static void test_rowoffset() {
+  const int K = 32, BN = 64, AR = 256;
+  std::mt19937 g(3);
+  std::vector<float> A((size_t)AR * K), B((size_t)BN * K), D((size_t)BM * BN);
+  for (auto& x : A) x = (float)((int)(g() % 9) - 4);
+  for (auto& x : B) x = (float)((int)(g() % 9) - 4);
+  float *dA, *dB, *dD;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dD, D.size() * 4));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CUtensorMap ma = make_map_2d(dA, AR, K, AR), mb = make_map_2d(dB, BN, K, BN);
+  const int smem = AR * 128 + BN * 128 + 2048;
+  CK(cudaFuncSetAttribute(probe_rowoffset, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int mode = 0; mode < 2; ++mode)
+    for (int sbo : {8, 10, 18})
+      for (int row0 : {0, 1, 3, 8, 11, 19}) {
+        if (row0 + 15 * sbo + 8 > AR) continue;
+        CK(cudaMemset(dD, 0xFF, D.size() * 4));
+        probe_rowoffset<<<1, 128, smem>>>(ma, mb, dD, row0, sbo, AR, mode);
+        CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+        size_t bad = 0;
+        for (int m = 0; m < BM; ++m) {
+          const int ar = row0 + (m / 8) * sbo + (m % 8);
+          for (int n = 0; n < BN; ++n) {
+            double s = 0; for (int k = 0; k < K; ++k) s += (double)A[(size_t)ar * K + k] * B[(size_t)n * K + k];
+            bad += ((double)D[(size_t)m * BN + n] != s);
+          }
+        }
+        printf("T6 rowoffset base_offset_field=%d sbo_rows=%2d row0=%2d: mismatches %zu %s\n", mode, sbo, row0, bad, bad ? "FAIL" : "ok");
+      }
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+}
+
 int main() {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   printf("device %s sm_%d%d SMs %d clock %d kHz\n", p.name, p.major, p.minor, p.multiProcessorCount, p.clockRate);
+  test_rowoffset();
+  if (getenv("PROBE_T6_ONLY")) return 0;
   test_exact<64>(); test_exact<128>(); test_exact<256>();
 
   std::mt19937 g(7); std::uniform_real_distribution<float> U(0.5f, 1.0f); std::normal_distribution<float> Nrm(0.f, 1.f);
