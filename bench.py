@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 S_VOL, RES = 300, 256
 GFLOP_PER_SLICE_TC = 96.20 - 0.0755  # all convs minus the 1->64 stem (CUDA cores); K=3
-WORKLOAD = "R231 (3-class) 300-slice 256x256 int16 synthetic CT volume per GPU, batch_size=20"
+WORKLOAD = "R231 (3-class) 300-slice 256x256 int16 synthetic CT volume per GPU, batch_size=20 (engine waves of 37 slices)"
 
 
 def log(*a):

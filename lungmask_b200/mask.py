@@ -114,9 +114,14 @@ class LMInferer:
         volume_postprocessing: bool = True,
         tqdm_disable: bool = False,
         device: Optional[int] = None,
+        wave_slices: Optional[int] = None,
     ):
         """Same arguments as the reference (lungmask/mask.py:72-82) plus `device` (CUDA ordinal, default
-        LOCAL_RANK or 0).  `batch_size` is the number of slices per forward wave on the device."""
+        LOCAL_RANK or 0) and `wave_slices`.  The reference's `batch_size` only bounds memory (slices are
+        independent, mask.py:172-187; the engine is batch-invariant, tests/test_gpu_forward.py); the engine
+        runs the forward in waves of `wave_slices` slices, default 37 when batch_size >= 20 because
+        37 x 16 tiles = 4 x 148 SMs fills every level of the U-Net with whole waves of CTAs (11.5 GB of
+        activations), else batch_size."""
         assert modelname in MODEL_URLS, "Modelname not found. Please choose from: {}".format(MODEL_URLS.keys())
         if fillmodel is not None:
             assert fillmodel in MODEL_URLS, "Modelname not found. Please choose from: {}".format(MODEL_URLS.keys())
@@ -138,7 +143,10 @@ class LMInferer:
         self.device = device
 
         self.model = get_model(self.modelname, modelpath)
-        self.engine = _native.Engine(device=device, batch_capacity=batch_size)
+        if wave_slices is None:
+            wave_slices = 37 if batch_size >= 20 else batch_size
+        self.wave_slices = wave_slices
+        self.engine = _native.Engine(device=device, batch_capacity=wave_slices)
         self.engine.load_weights(0, self.model.blob, self.model.n_classes)
         self.fillmodelm = None
         if self.fillmodel is not None:

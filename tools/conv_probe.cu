@@ -154,7 +154,8 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
     }
     // choose sample pixels: all for small problems, random subset otherwise
     const size_t npix = (size_t)N * plane;
-    const size_t nsamp = std::min<size_t>(npix, ints ? npix : 600);
+    const size_t budget = (size_t)(3e8 / ((double)L.Cout * Cin * L.taps)) + 8;  // bounded host work per layer
+    const size_t nsamp = std::min<size_t>(npix, ints ? npix : std::min<size_t>(600, budget));
     double max_err = 0, max_ref = 0; size_t bad = 0, label_bad = 0; double max_sc_err = 0, max_pool_err = 0;
     std::vector<double> yv(L.Cout);
     auto eval_pixel = [&](int n, int y, int x, std::vector<double>& out_y) {
@@ -233,6 +234,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
 }
 
 int main(int argc, char** argv) {
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   const int batch = argc > 1 ? atoi(argv[1]) : 8;
   const int chunk = argc > 2 ? atoi(argv[2]) : 4;
   const int timing_only = argc > 3 ? atoi(argv[3]) : 0;
@@ -241,10 +243,10 @@ int main(int argc, char** argv) {
   printf("device %s SMs %d; batch %d chunk_kb %d\n", prop.name, sms, batch, chunk);
   if (!timing_only) {
     const Layer small[] = {
-        {"ints 1tile", 8, 16, 32, 0, 64, 9, kModeReluBn, 0},
+        {"ints 1tile", 16, 8, 32, 0, 64, 9, kModeReluBn, 0},
         {"ints 128->128", 16, 32, 128, 0, 128, 9, kModeReluBn, 0},
         {"ints concat", 16, 16, 32, 32, 64, 9, kModeReluBn, 0},
-        {"ints 1x1", 8, 16, 64, 0, 128, 1, kModeLinear, 0},
+        {"ints 1x1", 16, 8, 64, 0, 128, 1, kModeLinear, 0},
     };
     for (const Layer& L : small) run_layer(L, 2, chunk, sms, true, true, 0);
     const Layer rnd[] = {
