@@ -30,14 +30,23 @@
 //     2*BN columns in a ring). The correction halves are NOT drained per chunk: each ring slot keeps
 //     accumulating its corrections for the whole tile (their drift is 2^-11 times smaller still) and is read
 //     once, with the slot's last chunk - so the per-chunk drain is BN columns, half of the accumulator.
-//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 MMA issuer, warp 2
-//     TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, two warps share a quarter and
+//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warps 1 and 3 MMA issuers
+//     (alternate chunks), warp 2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, two warps share a quarter and
 //     split the columns).
 #include <stdio.h>
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
 
 namespace lm {
+#ifdef LM_CONV_PROFILE
+// Role-level stall accounting for tools/conv_probe: cycles each role spends waiting on each barrier class.
+__device__ unsigned long long g_conv_prof[16];
+#define LM_PROF_T0() const long long prof_t0_ = clock64()
+#define LM_PROF_ADD(slot) atomicAdd(&g_conv_prof[slot], (unsigned long long)(clock64() - prof_t0_))
+#else
+#define LM_PROF_T0()
+#define LM_PROF_ADD(slot)
+#endif
 namespace {
 
 constexpr int BM = 128, BK = 32, TILE_H = 16, TILE_W = 8;
@@ -46,6 +55,7 @@ constexpr int A_PLANE_BYTES_3x3 = HALO_W * HALO_H * BK * 4;  // 180 rows x 128 B
 constexpr int A_PLANE_BYTES_1x1 = BM * BK * 4;               // 16 KB per plane
 constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB (both planes), 1024-aligned
 constexpr int NUM_A_BUFS = 2;
+constexpr int OUT_STAGE_BYTES = BM * 128;  // output staging per column half: 128 pixels x 32 channels fp32
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_THREADS = 256;
@@ -55,11 +65,11 @@ template <int BN>
 struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * B_PLANE_BYTES;      // one weight tile (hi + lo planes) per k-block
-  static constexpr int STAGES = (BN == 64) ? 6 : 4;
+  static constexpr int STAGES = (BN == 64) ? 6 : 3;
   static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
   static constexpr int NBUF = 512 / ACC_COLS;      // accumulator ring: 2 slots (BN=128), 4 slots (BN=64)
   static constexpr int TMEM_COLS = NBUF * ACC_COLS;
-  static constexpr int DYN_SMEM = NUM_A_BUFS * A_BUF_BYTES + STAGES * STAGE_BYTES + 1024;
+  static constexpr int DYN_SMEM = NUM_A_BUFS * A_BUF_BYTES + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;
 };
 
 struct TileCoord {
@@ -81,7 +91,8 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int n_tiles, int tile
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+               const __grid_constant__ CUtensorMap tmPool, const ConvParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr int NBUF = C::NBUF;
@@ -99,6 +110,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + NBUF]);
   const uint32_t afull0 = smem_u32(&bars[2 * STAGES + 2 * NBUF]), aempty0 = afull0 + 8 * NUM_A_BUFS;
   uint8_t* smem_b = smem + NUM_A_BUFS * A_BUF_BYTES;
+  uint8_t* smem_out = smem_b + STAGES * C::STAGE_BYTES;  // 2 x 16 KB, 1024-aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int tiles_x = p.W / TILE_W, tiles_img = tiles_x * (p.H / TILE_H);
@@ -112,13 +124,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int patch_w = TILE_W + 2 * halo;  // shared-memory rows per image row of the patch
   const int chunk_kb = p.chunk_kb;
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+  // Two MMA-issuing warps take alternate chunks when that is provably safe: an issuer does not observe the
+  // barrier phases of the k-blocks it skips, so it must never skip as many phases as a ring is deep
+  // (weight ring: chunk_kb <= STAGES-1; activation ring: every channel block must contain k-blocks of both
+  // issuers, i.e. 9 taps and chunk_kb < 9).  Otherwise warp 1 issues everything.
+  const bool dual_issue = (taps == 9) && (chunk_kb <= STAGES - 1);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < NUM_A_BUFS; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+    for (int s = 0; s < NUM_A_BUFS; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, dual_issue ? 2 : 1); }
     for (int b = 0; b < NBUF; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NUM_EPI_THREADS / 32); }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmPool);
   }
   if (warp == 2) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
   if (p.mode == kModeHead) {
@@ -129,81 +147,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+#ifdef LM_CONV_PROFILE
+  const long long prof_kernel_t0 = clock64();
+#endif
 
+  // Both single-issuer roles run as warp-uniform loops (all 32 lanes execute the control flow and poll the
+  // barriers, one elected lane issues the TMA / MMA / commit): loop state then lives in uniform registers
+  // and the issue thread is not throttled by divergent-code bookkeeping.
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t gkb = 0, ga = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(tile, n_tiles, tiles_x, tiles_img, BN);
-        for (int cb = 0; cb < num_cb; ++cb, ++ga) {
-          {  // the activation patch (+ halo) of this channel block, both planes, once for all taps
-            const uint32_t ab = ga % NUM_A_BUFS, aph = (ga / NUM_A_BUFS) & 1;
-            mbar_wait(aempty0 + 8 * ab, aph ^ 1);
-            mbar_arrive_expect_tx(afull0 + 8 * ab, 2 * a_plane_bytes);
-            const uint32_t dst = smem_u32(smem + ab * A_BUF_BYTES);
-            const int c = cb * BK;
-            if (c < p.C0) tma_load_5d(dst, &tmA0, afull0 + 8 * ab, c, t.x0 - halo, t.y0 - halo, 0, t.n);
-            else          tma_load_5d(dst, &tmA1, afull0 + 8 * ab, c - p.C0, t.x0 - halo, t.y0 - halo, 0, t.n);
-          }
-          for (int tap = 0; tap < taps; ++tap, ++gkb) {
-            const uint32_t s = gkb % STAGES, ph = (gkb / STAGES) & 1;
-            mbar_wait(empty0 + 8 * s, ph ^ 1);
+    uint32_t s = 0, ph = 0, ab = 0, aph = 0;
+    const uint32_t a_tx = 2u * (uint32_t)a_plane_bytes;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(tile, n_tiles, tiles_x, tiles_img, BN);
+      int c = 0;
+      for (int cb = 0; cb < num_cb; ++cb, c += BK) {
+        // the activation patch (+ halo) of this channel block, both planes, once for all taps
+        { LM_PROF_T0(); mbar_wait(aempty0 + 8 * ab, aph ^ 1); if (lane == 0) LM_PROF_ADD(0); }
+        if (elect_one()) {
+          mbar_arrive_expect_tx(afull0 + 8 * ab, a_tx);
+          const uint32_t dst = smem_u32(smem) + ab * A_BUF_BYTES;
+          if (c < p.C0) tma_load_5d(dst, &tmA0, afull0 + 8 * ab, c, t.x0 - halo, t.y0 - halo, 0, t.n);
+          else          tma_load_5d(dst, &tmA1, afull0 + 8 * ab, c - p.C0, t.x0 - halo, t.y0 - halo, 0, t.n);
+        }
+        __syncwarp();
+        if (++ab == NUM_A_BUFS) { ab = 0; aph ^= 1; }
+        for (int tap = 0; tap < taps; ++tap) {
+          { LM_PROF_T0(); mbar_wait(empty0 + 8 * s, ph ^ 1); if (lane == 0) LM_PROF_ADD(1); }
+          if (elect_one()) {
             mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
-            tma_load_4d(smem_u32(smem_b + s * C::STAGE_BYTES), &tmB, full0 + 8 * s, cb * BK, t.n0, tap, 0);
+            tma_load_4d(smem_u32(smem_b) + s * C::STAGE_BYTES, &tmB, full0 + 8 * s, c, t.n0, tap, 0);
           }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_wide = make_idesc_tf32(BM, 2 * BN), idesc_corr = make_idesc_tf32(BM, BN);
-      uint32_t gkb = 0, gc = 0, ga = 0;
-      const uint64_t sbo_field = (uint64_t)((patch_w * 128) >> 4) << 32;  // 8-row group stride = one patch row
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int kb = 0;
-        for (int c = 0; c < num_chunks; ++c, ++gc) {
-          const uint32_t buf = gc % NBUF, bph = (gc / NBUF) & 1;
-          mbar_wait(tempty0 + 8 * buf, bph ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
-          const int kend = min(num_kb, kb + chunk_kb);
-          bool first = true;                       // first k-step of the chunk: hi*hi restarts from zero
-          const uint32_t corr_acc = c >= NBUF;     // first use of this slot in the tile: corrections restart too
-          for (; kb < kend; ++kb, ++gkb) {
-            const int cb = kb / taps, tap = kb - cb * taps;
-            const uint32_t gcb = ga + cb;          // channel-block load this k-block reads
-            const uint32_t ab = gcb % NUM_A_BUFS, aph = (gcb / NUM_A_BUFS) & 1;
-            if (tap == 0) { mbar_wait(afull0 + 8 * ab, aph); }
-            const uint32_t s = gkb % STAGES, ph = (gkb / STAGES) & 1;
-            mbar_wait(full0 + 8 * s, ph);
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuers (two warps)
+    // A lone issuing thread is instruction-bound: next to the UTCHMMA stream every scalar instruction of the
+    // k-block bookkeeping costs ~10 cycles, and the tensor pipe idles whenever the thread is not inside an
+    // MMA issue (ncu: tensor pipe 31-56 % active with one issuer, profiles/r01_ncu_conv_single_issuer.md).
+    // Two warps on different SM sub-partitions therefore issue ALTERNATE chunks.  Chunk g (global count)
+    // lives in accumulator slot g % NBUF and NBUF is even, so each slot is only ever written by one issuer
+    // and the order of additions into every accumulator is fixed: results stay bit-deterministic.
+    const uint32_t me = (warp == 3) ? 1u : 0u;
+    const uint32_t idesc_wide = make_idesc_tf32(BM, 2 * BN), idesc_corr = make_idesc_tf32(BM, BN);
+    // shared-memory descriptors as (lo, hi) words: lo = start>>4 | LBO, hi = SBO | version | swizzle.
+    // A: K-major SW128 entered at an arbitrary 128-byte row, 8-row group stride = one patch row.
+    const uint32_t desc_hi_a = (uint32_t)((patch_w * 128) >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t desc_hi_b = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_base_lo = __shfl_sync(0xffffffffu, ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16), 0);
+    const uint32_t b_base_lo = __shfl_sync(0xffffffffu, ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16), 0);
+    const uint32_t a_lo_plane = (uint32_t)a_plane_bytes >> 4;
+    const uint32_t tap_row_step = (uint32_t)(patch_w - 2) * 8u;  // 16-byte units from (dy, dx=2) to (dy+1, dx=0)
+    const uint64_t hi_a = (uint64_t)desc_hi_a << 32, hi_b = (uint64_t)desc_hi_b << 32;
+    // walking state over ALL k-blocks of the CTA (both issuers walk the same sequence, each issues its own chunks)
+    uint32_t s = 0, ph = 0, ab = 0, aph = 0;
+    uint32_t b_lo = b_base_lo, a_lo_buf = a_base_lo;
+    uint32_t gc = 0;  // global chunk counter
+    for (int tile = blockIdx.x; tile < total_tiles && (dual_issue || me == 0u); tile += gridDim.x) {
+      int tap = 0, dx = 0;
+      uint32_t alo = a_lo_buf;
+      bool a_seen = false;  // this issuer has already waited for the current activation buffer
+      int kb = 0;
+      for (int c = 0; c < num_chunks; ++c, ++gc) {
+        const int kend = min(num_kb, kb + chunk_kb);
+        const bool mine = dual_issue ? ((gc & 1u) == me) : (me == 0u);
+        const uint32_t buf = gc % NBUF, bph = (gc / NBUF) & 1;
+        const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
+        if (mine) { LM_PROF_T0(); mbar_wait(tempty0 + 8 * buf, bph ^ 1); if (lane == 0) LM_PROF_ADD(2); }
+        bool first = true;                       // first k-step of the chunk: hi*hi restarts from zero
+        const uint32_t corr_acc = c >= NBUF;     // first use of this slot in the tile: corrections restart too
+        for (; kb < kend; ++kb) {
+          const bool last_tap = (tap == taps - 1);
+          if (mine) {
+            if (!a_seen) { LM_PROF_T0(); mbar_wait(afull0 + 8 * ab, aph); if (lane == 0) LM_PROF_ADD(3); a_seen = true; }
+            { LM_PROF_T0(); mbar_wait(full0 + 8 * s, ph); if (lane == 0) LM_PROF_ADD(4); }
             tc_fence_after();
-            const int dy = (taps == 9) ? tap / 3 : 0, dx = (taps == 9) ? tap % 3 : 0;  // already +1 (halo origin)
-            const uint32_t a_hi = smem_u32(smem + ab * A_BUF_BYTES) + (uint32_t)((dy * patch_w + dx) * 128);
-            // K-major SW128 descriptor entered at an arbitrary 128-byte row, row-group stride = patch row pitch
-            const uint64_t d_ahi = (make_smem_desc_sw128(a_hi) & ~((uint64_t)0x3FFF << 32)) | sbo_field;
-            const uint64_t d_alo = (make_smem_desc_sw128(a_hi + a_plane_bytes) & ~((uint64_t)0x3FFF << 32)) | sbo_field;
-            const uint64_t d_b = make_smem_desc_sw128(smem_u32(smem_b + s * C::STAGE_BYTES));  // B_hi rows, B_lo rows follow
-            const uint64_t d_blo = d_b + (uint64_t)(C::B_PLANE_BYTES >> 4);
-#pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              const uint64_t ko = (uint64_t)(k * 2);  // 8 tf32 = 32 B along K, >>4
+            LM_PROF_T0();
+            const bool last_kb = (kb == kend - 1);
+            if (elect_one()) {
               if (first) {
-                umma_tf32(d_tmem, d_ahi + ko, d_b + ko, idesc_corr, 0);               // hi*hi  := (zero init)
-                umma_tf32(d_tmem + BN, d_ahi + ko, d_blo + ko, idesc_corr, corr_acc);  // hi*lo
-                first = false;
+                umma_tf32_c<false>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_corr);                                          // hi*hi := (zero init)
+                umma_tf32(d_tmem + BN, hi_a | alo, hi_b | (b_lo + (uint32_t)(C::B_PLANE_BYTES >> 4)), idesc_corr, corr_acc);  // hi*lo
               } else {
-                umma_tf32(d_tmem, d_ahi + ko, d_b + ko, idesc_wide, 1);               // [hi*hi | hi*lo] +=
+                umma_tf32_c<true>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_wide);                                           // [hi*hi | hi*lo] +=
               }
-              umma_tf32(d_tmem + BN, d_alo + ko, d_b + ko, idesc_corr, 1);             // lo*hi into the right half
+              umma_tf32_c<true>(d_tmem + BN, hi_a | (alo + a_lo_plane), hi_b | b_lo, idesc_corr);                         // lo*hi
+#pragma unroll
+              for (int k = 1; k < BK / 8; ++k) {
+                const uint32_t ko = (uint32_t)(k * 2);  // 8 tf32 = 32 B along K, >>4
+                umma_tf32_c<true>(d_tmem, hi_a | (alo + ko), hi_b | (b_lo + ko), idesc_wide);
+                umma_tf32_c<true>(d_tmem + BN, hi_a | (alo + a_lo_plane + ko), hi_b | (b_lo + ko), idesc_corr);
+              }
+              umma_commit(empty0 + 8 * s);                  // weight stage consumed (only this issuer read it)
+              if (last_tap) umma_commit(aempty0 + 8 * ab);  // this issuer is done with the activation buffer
+              if (last_kb) umma_commit(tfull0 + 8 * buf);   // chunk complete -> epilogue may drain it
             }
-            umma_commit(empty0 + 8 * s);
-            if (tap == taps - 1) umma_commit(aempty0 + 8 * ab);  // all taps of this channel block issued
+            __syncwarp();
+            if (lane == 0) LM_PROF_ADD(5);
+            first = false;
+          } else if (last_tap && dual_issue) {
+            // not my k-block, but both issuers release every activation buffer (barrier count 2); the commit
+            // arrives once MY earlier MMAs (which may have read the buffer) have retired
+            if (elect_one()) umma_commit(aempty0 + 8 * ab);
+            __syncwarp();
           }
-          umma_commit(tfull0 + 8 * buf);
+          if (++s == STAGES) { s = 0; ph ^= 1; b_lo = b_base_lo; } else b_lo += (uint32_t)(C::STAGE_BYTES >> 4);
+          if (last_tap) {
+            tap = 0; dx = 0; a_seen = false;
+            if (++ab == NUM_A_BUFS) { ab = 0; aph ^= 1; a_lo_buf = a_base_lo; } else a_lo_buf += (uint32_t)(A_BUF_BYTES >> 4);
+            alo = a_lo_buf;
+          } else {
+            ++tap;
+            if (++dx == 3) { dx = 0; alo += tap_row_step; } else alo += 8u;
+          }
         }
-        ga += num_cb;
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -212,50 +272,88 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int row = q * 32 + lane, hl = row >> 3, wl = row & 7;  // 16 x 8 patch, 8 pixels per image row
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const size_t plane = (size_t)p.H * p.W * p.Cout;
-    uint32_t gc = 0;
+    uint32_t buf = 0, bph = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(tile, n_tiles, tiles_x, tiles_img, BN);
       float acc[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) acc[i] = 0.f;
-      for (int c = 0; c < num_chunks; ++c, ++gc) {
-        const uint32_t buf = gc % NBUF, bph = (gc / NBUF) & 1;
-        mbar_wait(tfull0 + 8 * buf, bph);
+      for (int c = 0; c < num_chunks; ++c) {
+        { LM_PROF_T0(); mbar_wait(tfull0 + 8 * buf, bph); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
         tc_fence_after();
+        LM_PROF_T0();
         const uint32_t col0 = tmem_base + lane_base + buf * C::ACC_COLS + half * NC;
         const bool last_use = c >= num_chunks - NBUF;  // this slot is not written again in this tile
+        // all TMEM reads of this slot first, then hand the slot back BEFORE the register adds: the
+        // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
+        float v[NC];
 #pragma unroll
-        for (int j = 0; j < NC / 32; ++j) {
-          float v[32];
-          tmem_ld32(col0 + j * 32, v);               // hi*hi partial sums of this chunk
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[j * 32 + i] += v[i];
-        }
+        for (int j = 0; j < NC / 32; ++j) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
         if (last_use) {
+          float w[NC];
 #pragma unroll
-          for (int j = 0; j < NC / 32; ++j) {
-            float w[32];
-            tmem_ld32(col0 + BN + j * 32, w);        // the slot's hi*lo + lo*hi corrections, whole tile
-            tmem_ld_wait();
+          for (int j = 0; j < NC / 32; ++j) tmem_ld32(col0 + BN + j * 32, w + j * 32);  // the slot's corrections, whole tile
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[j * 32 + i] += w[i];
-          }
+          for (int i = 0; i < NC; ++i) acc[i] = (acc[i] + v[i]) + w[i];
+        } else {
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+#pragma unroll
+          for (int i = 0; i < NC; ++i) acc[i] += v[i];
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(7);
+        if (++buf == NBUF) { buf = 0; bph ^= 1; }
       }
+      LM_PROF_T0();
       const int y = t.y0 + hl, x = t.x0 + wl;
       const int cbase = t.n0 + half * NC;
       const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
 
-      if (p.mode == kModeLinear) {
-        float4* o = reinterpret_cast<float4*>(p.out + (((size_t)t.n * p.H + y) * p.W + x) * p.Cout + cbase);
+      // The tile leaves through shared memory: every thread drops its pixel's 32-channel groups as 128-byte
+      // rows (128B-swizzled, conflict-free) into its column half's 16 KB staging buffer, and one elected
+      // thread per half hands the buffer to a TMA store - fully coalesced 128 B bursts instead of 32 scattered
+      // 16-byte stores per warp instruction (which cost 16-23k cycles per tile, profiles/r01_conv_role_stalls_v2.log).
+      const uint32_t stage = smem_u32(smem_out) + half * OUT_STAGE_BYTES;
+      const bool issuer = (q == 0) && (lane == 0);
+      const int bar_id = 2 + half;
+      auto stage_row = [&](uint32_t r, const float* v8x4) {  // 32 floats -> row r, chunk j at (j ^ (r & 7))
 #pragma unroll
-        for (int i = 0; i < NC / 4; ++i) {
-          const float4 b = __ldg(bias4 + i);
-          o[i] = make_float4(acc[4 * i] + b.x, acc[4 * i + 1] + b.y, acc[4 * i + 2] + b.z, acc[4 * i + 3] + b.w);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stage + r * 128u + (uint32_t)((j ^ (int)(r & 7u)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v8x4[4 * j]), "f"(v8x4[4 * j + 1]),
+                       "f"(v8x4[4 * j + 2]), "f"(v8x4[4 * j + 3])
+                       : "memory");
+        }
+      };
+      auto round_begin = [&]() {
+        if (issuer) tma_store_wait_read();  // the previous store has finished reading the buffer
+        named_bar_sync(bar_id, 128);
+      };
+      auto round_end = [&]() {
+        fence_proxy_async();
+        named_bar_sync(bar_id, 128);
+      };
+
+      if (p.mode == kModeLinear) {
+#pragma unroll
+        for (int g = 0; g < NC / 32; ++g) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + g * 8 + i);
+            v[4 * i] = acc[g * 32 + 4 * i] + b.x; v[4 * i + 1] = acc[g * 32 + 4 * i + 1] + b.y;
+            v[4 * i + 2] = acc[g * 32 + 4 * i + 2] + b.z; v[4 * i + 3] = acc[g * 32 + 4 * i + 3] + b.w;
+          }
+          round_begin();
+          stage_row((uint32_t)row, v);
+          round_end();
+          if (issuer) { tma_store_4d(&tmOut, stage, cbase + g * 32, t.x0, t.y0, t.n); tma_store_commit(); }
         }
       } else {
         const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cbase);
@@ -312,50 +410,64 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           named_bar_sync(1, NUM_EPI_THREADS);
         } else {
-          float* o_hi = p.out + ((((size_t)t.n * 2) * p.H + y) * p.W + x) * p.Cout + cbase;
-          float* o_lo = o_hi + plane;
 #pragma unroll
-          for (int i = 0; i < NC / 4; ++i) {
-            float4 hi, lo;
-            split_tf32(acc[4 * i + 0], hi.x, lo.x);
-            split_tf32(acc[4 * i + 1], hi.y, lo.y);
-            split_tf32(acc[4 * i + 2], hi.z, lo.z);
-            split_tf32(acc[4 * i + 3], hi.w, lo.w);
-            reinterpret_cast<float4*>(o_hi)[i] = hi;
-            reinterpret_cast<float4*>(o_lo)[i] = lo;
+          for (int g = 0; g < NC / 32; ++g) {
+#pragma unroll
+            for (int plane = 0; plane < 2; ++plane) {
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float hi, lo;
+                split_tf32(acc[g * 32 + i], hi, lo);
+                v[i] = plane ? lo : hi;
+              }
+              round_begin();
+              stage_row((uint32_t)row, v);
+              round_end();
+              if (issuer) { tma_store_5d(&tmOut, stage, cbase + g * 32, t.x0, t.y0, plane, t.n); tma_store_commit(); }
+            }
           }
           if (p.mode == kModeReluBnPool) {
-            // 2x2 average (resunet.py:64): partners are lanes ^1 (x) and ^8 (y) of the same warp.
-            const int Hp = p.H >> 1, Wp = p.W >> 1;
+            // 2x2 average (resunet.py:64): partners are lanes ^1 (x) and ^8 (y) of the same warp; the lane with
+            // even x and y stages the pooled pixel: 8 per warp, 32 per column half = rows 0..31 of the buffer.
             const bool writer = (lane & 9) == 0;
-            float* q_hi = p.out_pool + ((((size_t)t.n * 2) * Hp + (y >> 1)) * Wp + (x >> 1)) * p.Cout + cbase;
-            float* q_lo = q_hi + (size_t)Hp * Wp * p.Cout;
+            const uint32_t prow = (uint32_t)((hl >> 1) * (TILE_W / 2) + (wl >> 1));
 #pragma unroll
-            for (int i = 0; i < NC / 4; ++i) {
-              float v[4];
+            for (int g = 0; g < NC / 32; ++g) {
+              float pv[32];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float s = acc[4 * i + e] + __shfl_xor_sync(0xffffffffu, acc[4 * i + e], 1);
+              for (int i = 0; i < 32; ++i) {
+                float s = acc[g * 32 + i] + __shfl_xor_sync(0xffffffffu, acc[g * 32 + i], 1);
                 s = s + __shfl_xor_sync(0xffffffffu, s, 8);
-                v[e] = s * 0.25f;
+                pv[i] = s * 0.25f;
               }
-              if (writer) {
-                float4 hi, lo;
-                split_tf32(v[0], hi.x, lo.x);
-                split_tf32(v[1], hi.y, lo.y);
-                split_tf32(v[2], hi.z, lo.z);
-                split_tf32(v[3], hi.w, lo.w);
-                reinterpret_cast<float4*>(q_hi)[i] = hi;
-                reinterpret_cast<float4*>(q_lo)[i] = lo;
+#pragma unroll
+              for (int plane = 0; plane < 2; ++plane) {
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  float hi, lo;
+                  split_tf32(pv[i], hi, lo);
+                  v[i] = plane ? lo : hi;
+                }
+                round_begin();
+                if (writer) stage_row(prow, v);
+                round_end();
+                if (issuer) { tma_store_5d(&tmPool, stage, cbase + g * 32, t.x0 >> 1, t.y0 >> 1, plane, t.n); tma_store_commit(); }
               }
             }
           }
         }
       }
+      if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(8);
     }
+    if ((warp & 3) == 0 && lane == 0) tma_store_wait_all();  // the two issuers: global writes complete before exit
   }
   tc_fence_before();
   __syncthreads();
+#ifdef LM_CONV_PROFILE
+  if (threadIdx.x == 0) atomicAdd(&g_conv_prof[9], (unsigned long long)(clock64() - prof_kernel_t0));
+#endif
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -410,6 +522,34 @@ int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const f
   r = (p.C1 > 0) ? make_act_map(&maps->a1, src1, n_capacity, p.H, p.W, p.C1, p.taps)
                  : make_act_map(&maps->a1, src0, n_capacity, p.H, p.W, p.C0, p.taps);
   if (r) return r;
+  // TMA-store maps: one 32-channel x 8 x 16 pixel box of one plane per store
+  if (p.mode == kModeReluBn || p.mode == kModeReluBnPool) {
+    cuuint64_t od[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, 2, (cuuint64_t)n_capacity};
+    cuuint64_t os[4] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4,
+                        (cuuint64_t)2 * p.H * p.W * p.Cout * 4};
+    cuuint32_t ob[5] = {BK, TILE_W, TILE_H, 1, 1};
+    r = encode(&maps->out, p.out, 5, od, os, ob);
+    if (r) return r;
+  } else if (p.mode == kModeLinear) {
+    cuuint64_t od[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n_capacity};
+    cuuint64_t os[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4};
+    cuuint32_t ob[4] = {BK, TILE_W, TILE_H, 1};
+    r = encode(&maps->out, p.out, 4, od, os, ob);
+    if (r) return r;
+  } else {
+    maps->out = maps->a0;
+  }
+  if (p.mode == kModeReluBnPool) {
+    const int Hp = p.H / 2, Wp = p.W / 2;
+    cuuint64_t od[5] = {(cuuint64_t)p.Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, 2, (cuuint64_t)n_capacity};
+    cuuint64_t os[4] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)Wp * p.Cout * 4, (cuuint64_t)Hp * Wp * p.Cout * 4,
+                        (cuuint64_t)2 * Hp * Wp * p.Cout * 4};
+    cuuint32_t ob[5] = {BK, TILE_W / 2, TILE_H / 2, 1, 1};
+    r = encode(&maps->pool, p.out_pool, 5, od, os, ob);
+    if (r) return r;
+  } else {
+    maps->pool = maps->a0;
+  }
   const int Cin = p.C0 + p.C1;
   cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)p.Cout, (cuuint64_t)p.taps, 2};
   cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)p.Cout * Cin * 4, (cuuint64_t)p.taps * p.Cout * Cin * 4};
@@ -428,9 +568,14 @@ static int launch_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, c
   }
   const int total = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN);
   const int grid = total < num_sms ? total : num_sms;
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::DYN_SMEM, stream>>>(maps.a0, maps.a1, maps.b, p);
+  conv_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::DYN_SMEM, stream>>>(maps.a0, maps.a1, maps.b, maps.out, maps.pool, p);
   return (int)cudaGetLastError();
 }
+
+#ifdef LM_CONV_PROFILE
+void conv_prof_reset() { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z)); }
+void conv_prof_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_conv_prof, 16 * sizeof(unsigned long long)); }
+#endif
 
 int launch_conv_tc(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   if (p.mode == kModeHead && (p.Cout != 64 || p.K > MAX_CLASSES)) return -4;

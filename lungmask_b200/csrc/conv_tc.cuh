@@ -41,6 +41,7 @@ struct ConvParams {
 // Tensor maps for one launch (built once per layer by make_conv_maps).
 struct ConvMaps {
   CUtensorMap a0, a1, b;
+  CUtensorMap out, pool;  // TMA-store maps of the output tile (mode 0/1/2) and of the pooled tile (mode 1)
 };
 
 // Builds the TMA descriptors. src1 may be nullptr when C1 == 0. Returns 0 on success.

@@ -20,6 +20,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
                                                    const float* __restrict__ shift,  // [64]
                                                    int N, int H, int W) {
   __shared__ float sw[64 * 9], sb[64], ss[64], sh[64];
+  // (hu + 1024) / 1624 for every HU value the pre-processing can produce ([-1024, 600]): float64 division, then
+  // the cast to fp32 (mask.py:168,178-182), tabulated once per block instead of nine fp64 divisions per thread
+  __shared__ float lut[1625];
+  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = (float)((double)i / 1624.0);
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) { sb[threadIdx.x] = bias[threadIdx.x]; ss[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
@@ -39,7 +43,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
         int hu = in[(size_t)n * plane + (size_t)yy * W + xx];
         hu = hu > 600 ? 600 : hu;  // mask.py:167 (no-op after the clip in utils.py:45)
-        val = (float)((double)(hu + 1024) / 1624.0);  // mask.py:168 in float64, cast to fp32 at :178-182
+        const int idx = hu + 1024;
+        val = idx >= 0 ? lut[idx] : (float)((double)idx / 1624.0);  // mask.py:168 (values below -1024 never come out of preprocess)
       }
       v[tap] = val;
     }

@@ -12,6 +12,9 @@
 #include "../lungmask_b200/csrc/conv_tc.cuh"
 
 using namespace lm;
+#ifdef LM_CONV_PROFILE
+namespace lm { void conv_prof_reset(); void conv_prof_read(unsigned long long*); }
+#endif
 
 #define CK(x)                                                                         \
   do {                                                                                \
@@ -133,6 +136,9 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   if (r) { printf("launch failed %d\n", r); exit(2); }
   CK(cudaDeviceSynchronize());
   float ms = 0;
+#ifdef LM_CONV_PROFILE
+  conv_prof_reset();
+#endif
   if (reps > 0) {
     CK(cudaEventRecord(e0));
     for (int i = 0; i < reps; ++i) launch_conv_tc(maps, p, num_sms, 0);
@@ -225,6 +231,18 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
     if (L.mode == kModeHead) printf(" score_err=%.3e label_mismatch(margin>1e-4)=%zu", max_sc_err, label_bad);
     printf(" %s\n", (bad || label_bad || max_pool_err > 1e-4 || max_sc_err > 1e-4) ? "FAIL" : "ok");
   }
+#ifdef LM_CONV_PROFILE
+  if (reps > 0) {
+    unsigned long long pr[16]; conv_prof_read(pr);
+    const int BNt = conv_tile_n(L.Cout);
+    const double tiles = (double)N * (L.H / 16) * (L.W / 8) * (L.Cout / BNt) * reps;
+    const double kbs = tiles * (Cin / 32) * L.taps;
+    const double ctas = std::min<double>(num_sms, tiles / reps) * reps;
+    printf("PROF  %-18s per k-block cycles: kernel %.0f | producer wait aempty %.0f bempty %.0f | mma wait tempty %.0f afull %.0f bfull %.0f issue %.0f | epi wait tfull %.0f drain %.0f, tile-epilogue per tile %.0f\n",
+           L.name, pr[9] / kbs * 1.0 * 1, pr[0] / kbs, pr[1] / kbs, pr[2] / kbs, pr[3] / kbs, pr[4] / kbs, pr[5] / kbs, pr[6] / kbs, pr[7] / kbs, pr[8] / tiles);
+    (void)ctas;
+  }
+#endif
   if (reps > 0)
     printf("TIME  %-22s N=%d %3dx%-3d C=%4d+%-4d->%4d taps=%d: %.3f ms  %.1f TFLOP/s(algorithmic)\n", L.name, N, L.H, L.W,
            L.C0, L.C1, L.Cout, L.taps, ms, flops / ms * 1e-9);

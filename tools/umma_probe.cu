@@ -186,6 +186,62 @@ probe_rowoffset(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 64); }
 }
 
+// T8: raw kind::tf32 MMA stream from resident shared-memory operands, issued the CUTLASS way: the whole warp
+// runs the loop (uniform control flow, operands computed outside the elected region), only the tcgen05
+// instructions sit under elect_one.  Measures the per-instruction issue floor for N = 64 / 128 / 256.
+template <int N>
+__global__ void __launch_bounds__(128, 1)
+probe_issue_uniform(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int iters,
+                    int commit, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[3];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t full = smem_u32(&bars[0]), dummy = smem_u32(&bars[1]), done = smem_u32(&bars[2]);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { mbar_init(full, 1); mbar_init(dummy, 1); mbar_init(done, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), 256);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (warp == 1) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(full, 128 * 128 + N * 128);
+      tma_load_2d(smem_u32(smem), &tmA, full, 0, 0);
+      tma_load_2d(smem_u32(smem) + 128 * 128, &tmB, full, 0, 0);
+    }
+    __syncwarp();
+    mbar_wait(full, 0);
+    tc_fence_after();
+    const uint64_t adesc = make_smem_desc_sw128(smem_u32(smem));
+    const uint64_t bdesc = make_smem_desc_sw128(smem_u32(smem) + 128 * 128);
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      // optional per-k-block extras on the issuing warp: bit1 = wait on an already-completed barrier phase,
+      // bit2 = tcgen05.fence::after_thread_sync, bit3 = a second completed-barrier wait
+      if (commit & 2) mbar_wait(full, 0);
+      if (commit & 8) mbar_wait(full, 0);
+      if (commit & 4) tc_fence_after();
+      if (elect_one()) {
+        umma_tf32_c<true>(tmem_base, adesc, bdesc, idesc);
+        umma_tf32_c<true>(tmem_base, adesc + 2, bdesc + 2, idesc);
+        umma_tf32_c<true>(tmem_base, adesc + 4, bdesc + 4, idesc);
+        umma_tf32_c<true>(tmem_base, adesc + 6, bdesc + 6, idesc);
+        if (commit & 1) umma_commit(dummy);
+      }
+      __syncwarp();
+    }
+    const long long t1 = clock64();
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
+    mbar_wait(done, 0);
+    const long long t2 = clock64();
+    if (threadIdx.x == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  }
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -275,6 +331,28 @@ static void test_exact() {
 }
 
 
+
+template <int N>
+static void test_issue_uniform() {
+  const int K = 32;
+  std::vector<float> A((size_t)128 * K, 1.f), B((size_t)N * K, 1.f);
+  float *dA, *dB; long long* dT;
+  CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dT, 16));
+  CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+  CUtensorMap ma = make_map_2d(dA, 128, K, 128), mb = make_map_2d(dB, N, K, N);
+  const int smem = 128 * 128 + N * 128 + 2048;
+  CK(cudaFuncSetAttribute(probe_issue_uniform<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int commit : {0, 1, 3, 5, 7, 15}) {
+    long long t[2];
+    probe_issue_uniform<N><<<1, 128, smem>>>(ma, mb, 4096, commit, dT);
+    CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(t, dT, 16, cudaMemcpyDeviceToHost));
+    printf("T8 N=%3d uniform-issue, per-k-block extras mask=%2d (1 commit, 2 ready-barrier wait, 4 tcgen05 fence, 8 second wait): %.1f cycles per k-block (4 MMAs of 128xNx8) [ideal %.0f]\n", N, commit, (double)t[1] / 4096, 4.0 * N / 2.0);
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dT);
+}
+
 static void test_rowoffset() {
   const int K = 32, BN = 64, AR = 256;
   std::mt19937 g(3);
@@ -313,6 +391,7 @@ int main() {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   printf("device %s sm_%d%d SMs %d clock %d kHz\n", p.name, p.major, p.minor, p.multiProcessorCount, p.clockRate);
   test_rowoffset();
+  test_issue_uniform<64>(); test_issue_uniform<128>(); test_issue_uniform<256>();
   if (getenv("PROBE_T6_ONLY")) return 0;
   test_exact<64>(); test_exact<128>(); test_exact<256>();
 
