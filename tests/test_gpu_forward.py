@@ -144,3 +144,18 @@ def test_activation_taps(engine, models):
         print("%-3s max|d|/max|x| = %.3e" % (name, rel))
         worst = max(worst, rel)
     assert worst < 2e-5
+
+
+def test_default_wave_matches_small_waves(engine, models, tmp_path):
+    """LMInferer's default 37-slice forward wave (one full wave + a 2-slice tail) gives bit-identical labels to
+    the capacity-4 engine: the engine is batch-invariant, so the reference's batch_size only bounds memory."""
+    import torch
+    from lungmask_b200 import LMInferer
+    p = str(tmp_path / "w3.pth")
+    torch.save(models[3], p)
+    inf = LMInferer(modelpath=p, tqdm_disable=True)
+    assert inf.wave_slices == 37 and inf.batch_size == 20
+    vol = synth.phantom(39, seed=77)
+    m = _blob(models[3])
+    engine.load_weights(0, m.blob, m.n_classes)
+    assert np.array_equal(inf.apply(vol), engine.apply_volume(0, vol))
