@@ -55,7 +55,7 @@ constexpr int A_PLANE_BYTES_3x3 = HALO_W * HALO_H * BK * 4;  // 180 rows x 128 B
 constexpr int A_PLANE_BYTES_1x1 = BM * BK * 4;               // 16 KB per plane
 constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB (both planes), 1024-aligned
 constexpr int NUM_A_BUFS = 2;
-constexpr int OUT_STAGE_BYTES = BM * 128;  // output staging per column half: 128 pixels x 32 channels fp32
+constexpr int OUT_STAGE_BYTES = BM * 128;  // output staging: 8 epilogue warps x 4 KB (32 pixels x 32 channels fp32), x2 halves
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_THREADS = 256;
@@ -316,12 +316,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
 
       // The tile leaves through shared memory: every thread drops its pixel's 32-channel groups as 128-byte
-      // rows (128B-swizzled, conflict-free) into its column half's 16 KB staging buffer, and one elected
-      // thread per half hands the buffer to a TMA store - fully coalesced 128 B bursts instead of 32 scattered
-      // 16-byte stores per warp instruction (which cost 16-23k cycles per tile, profiles/r01_conv_role_stalls_v2.log).
-      const uint32_t stage = smem_u32(smem_out) + half * OUT_STAGE_BYTES;
-      const bool issuer = (q == 0) && (lane == 0);
-      const int bar_id = 2 + half;
+      // rows (128B-swizzled, conflict-free) into its WARP's 4 KB staging buffer (32 pixels = 4 image rows x 8)
+      // and the warp's lane 0 hands the buffer to a TMA store - fully coalesced 128 B bursts instead of 32
+      // scattered 16-byte stores per warp instruction (16-23k cycles per tile, profiles/r01_conv_role_stalls_v2.log)
+      // - with no cross-warp barrier: each epilogue warp streams its own rows out independently.
+      const uint32_t stage = smem_u32(smem_out) + (uint32_t)(warp - EPI_WARP0) * 4096u;
+      const bool issuer = (lane == 0);
+      const int ty0 = t.y0 + 4 * q;  // first image row of this warp's 32 pixels
       auto stage_row = [&](uint32_t r, const float* v8x4) {  // 32 floats -> row r, chunk j at (j ^ (r & 7))
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -332,12 +333,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
       };
       auto round_begin = [&]() {
-        if (issuer) tma_store_wait_read();  // the previous store has finished reading the buffer
-        named_bar_sync(bar_id, 128);
+        if (issuer) tma_store_wait_read();  // this warp's previous store has finished reading the buffer
+        __syncwarp();
       };
       auto round_end = [&]() {
         fence_proxy_async();
-        named_bar_sync(bar_id, 128);
+        __syncwarp();
       };
 
       if (p.mode == kModeLinear) {
@@ -351,9 +352,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             v[4 * i + 2] = acc[g * 32 + 4 * i + 2] + b.z; v[4 * i + 3] = acc[g * 32 + 4 * i + 3] + b.w;
           }
           round_begin();
-          stage_row((uint32_t)row, v);
+          stage_row((uint32_t)lane, v);
           round_end();
-          if (issuer) { tma_store_4d(&tmOut, stage, cbase + g * 32, t.x0, t.y0, t.n); tma_store_commit(); }
+          if (issuer) { tma_store_4d(&tmOut, stage, cbase + g * 32, t.x0, ty0, t.n); tma_store_commit(); }
         }
       } else {
         const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cbase);
@@ -422,16 +423,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 v[i] = plane ? lo : hi;
               }
               round_begin();
-              stage_row((uint32_t)row, v);
+              stage_row((uint32_t)lane, v);
               round_end();
-              if (issuer) { tma_store_5d(&tmOut, stage, cbase + g * 32, t.x0, t.y0, plane, t.n); tma_store_commit(); }
+              if (issuer) { tma_store_5d(&tmOut, stage, cbase + g * 32, t.x0, ty0, plane, t.n); tma_store_commit(); }
             }
           }
           if (p.mode == kModeReluBnPool) {
             // 2x2 average (resunet.py:64): partners are lanes ^1 (x) and ^8 (y) of the same warp; the lane with
-            // even x and y stages the pooled pixel: 8 per warp, 32 per column half = rows 0..31 of the buffer.
+            // even x and y stages the pooled pixel: 8 per warp (2 pooled rows x 4) = rows 0..7 of the warp's buffer.
             const bool writer = (lane & 9) == 0;
-            const uint32_t prow = (uint32_t)((hl >> 1) * (TILE_W / 2) + (wl >> 1));
+            const uint32_t prow = (uint32_t)((lane >> 4) * (TILE_W / 2) + ((lane & 7) >> 1));
 #pragma unroll
             for (int g = 0; g < NC / 32; ++g) {
               float pv[32];
@@ -453,7 +454,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                 round_begin();
                 if (writer) stage_row(prow, v);
                 round_end();
-                if (issuer) { tma_store_5d(&tmPool, stage, cbase + g * 32, t.x0 >> 1, t.y0 >> 1, plane, t.n); tma_store_commit(); }
+                if (issuer) { tma_store_5d(&tmPool, stage, cbase + g * 32, t.x0 >> 1, ty0 >> 1, plane, t.n); tma_store_commit(); }
               }
             }
           }
@@ -461,7 +462,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(8);
     }
-    if ((warp & 3) == 0 && lane == 0) tma_store_wait_all();  // the two issuers: global writes complete before exit
+    if (lane == 0) tma_store_wait_all();  // every epilogue warp's issuer: global writes complete before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -522,18 +523,18 @@ int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const f
   r = (p.C1 > 0) ? make_act_map(&maps->a1, src1, n_capacity, p.H, p.W, p.C1, p.taps)
                  : make_act_map(&maps->a1, src0, n_capacity, p.H, p.W, p.C0, p.taps);
   if (r) return r;
-  // TMA-store maps: one 32-channel x 8 x 16 pixel box of one plane per store
+  // TMA-store maps: one epilogue warp's rows per store
   if (p.mode == kModeReluBn || p.mode == kModeReluBnPool) {
     cuuint64_t od[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, 2, (cuuint64_t)n_capacity};
     cuuint64_t os[4] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4,
                         (cuuint64_t)2 * p.H * p.W * p.Cout * 4};
-    cuuint32_t ob[5] = {BK, TILE_W, TILE_H, 1, 1};
+    cuuint32_t ob[5] = {BK, TILE_W, 4, 1, 1};  // one epilogue warp: 32 channels x 8 x 4 pixels of one plane
     r = encode(&maps->out, p.out, 5, od, os, ob);
     if (r) return r;
   } else if (p.mode == kModeLinear) {
     cuuint64_t od[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n_capacity};
     cuuint64_t os[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4};
-    cuuint32_t ob[4] = {BK, TILE_W, TILE_H, 1};
+    cuuint32_t ob[4] = {BK, TILE_W, 4, 1};
     r = encode(&maps->out, p.out, 4, od, os, ob);
     if (r) return r;
   } else {
@@ -544,7 +545,7 @@ int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const f
     cuuint64_t od[5] = {(cuuint64_t)p.Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, 2, (cuuint64_t)n_capacity};
     cuuint64_t os[4] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)Wp * p.Cout * 4, (cuuint64_t)Hp * Wp * p.Cout * 4,
                         (cuuint64_t)2 * Hp * Wp * p.Cout * 4};
-    cuuint32_t ob[5] = {BK, TILE_W / 2, TILE_H / 2, 1, 1};
+    cuuint32_t ob[5] = {BK, TILE_W / 2, 2, 1, 1};
     r = encode(&maps->pool, p.out_pool, 5, od, os, ob);
     if (r) return r;
   } else {
