@@ -69,6 +69,12 @@ struct Cfg {
   static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
   static constexpr int NBUF = 512 / ACC_COLS;      // accumulator ring: 2 slots (BN=128), 4 slots (BN=64)
   static constexpr int TMEM_COLS = NBUF * ACC_COLS;
+  // Epilogue organisation.  BN = 128: the 8 epilogue warps split every tile's columns in two halves (64 per thread).
+  // BN = 64: a thread can hold a full row (64 columns), so the warps form TWO GROUPS that take alternate tiles:
+  // while one group runs the tile-end epilogue (BN, split, TMA stores - a third of a short 18-k-block tile), the
+  // other already drains the next tile's chunks and the tensor pipe never waits for a free accumulator slot.
+  static constexpr int HALVES = (BN == 64) ? 1 : 2;
+  static constexpr int EGROUPS = (BN == 64) ? 2 : 1;
   static constexpr int DYN_SMEM = NUM_A_BUFS * A_BUF_BYTES + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;
 };
 
@@ -96,19 +102,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr int NBUF = C::NBUF;
-  constexpr int NC = BN / 2;  // accumulator columns held by one epilogue thread
+  constexpr int HALVES = C::HALVES, EGROUPS = C::EGROUPS;
+  constexpr int NC = BN / HALVES;  // accumulator columns held by one epilogue thread (64)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * NBUF + 2 * NUM_A_BUFS];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + (EGROUPS + 1) * NBUF + 2 * NUM_A_BUFS];
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_head_w[MAX_CLASSES * 64];
   __shared__ float s_head_b[MAX_CLASSES];
-  __shared__ float s_part[BM][MAX_CLASSES];
 
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + NBUF]);
-  const uint32_t afull0 = smem_u32(&bars[2 * STAGES + 2 * NBUF]), aempty0 = afull0 + 8 * NUM_A_BUFS;
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + EGROUPS * NBUF]);
+  const uint32_t afull0 = smem_u32(&bars[2 * STAGES + (EGROUPS + 1) * NBUF]), aempty0 = afull0 + 8 * NUM_A_BUFS;
   uint8_t* smem_b = smem + NUM_A_BUFS * A_BUF_BYTES;
   uint8_t* smem_out = smem_b + STAGES * C::STAGE_BYTES;  // 2 x 16 KB, 1024-aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,7 +139,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < NUM_A_BUFS; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, dual_issue ? 2 : 1); }
-    for (int b = 0; b < NBUF; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, NUM_EPI_THREADS / 32); }
+    for (int b = 0; b < EGROUPS * NBUF; ++b) mbar_init(tfull0 + 8 * b, 1);
+    for (int b = 0; b < NBUF; ++b) mbar_init(tempty0 + 8 * b, NUM_EPI_THREADS / 32 / EGROUPS);
     fence_mbar_init();
     tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmPool);
@@ -206,7 +213,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t s = 0, ph = 0, ab = 0, aph = 0;
     uint32_t b_lo = b_base_lo, a_lo_buf = a_base_lo;
     uint32_t gc = 0;  // global chunk counter
-    for (int tile = blockIdx.x; tile < total_tiles && (dual_issue || me == 0u); tile += gridDim.x) {
+    uint32_t tseq = 0;  // tiles processed by this CTA: the epilogue group (BN = 64) of a tile is tseq & 1
+    for (int tile = blockIdx.x; tile < total_tiles && (dual_issue || me == 0u); tile += gridDim.x, ++tseq) {
+      const uint32_t tfull_t = tfull0 + 8 * ((EGROUPS == 2 ? (tseq & 1u) : 0u) * NBUF);
       int tap = 0, dx = 0;
       uint32_t alo = a_lo_buf;
       bool a_seen = false;  // this issuer has already waited for the current activation buffer
@@ -243,7 +252,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               }
               umma_commit(empty0 + 8 * s);                  // weight stage consumed (only this issuer read it)
               if (last_tap) umma_commit(aempty0 + 8 * ab);  // this issuer is done with the activation buffer
-              if (last_kb) umma_commit(tfull0 + 8 * buf);   // chunk complete -> epilogue may drain it
+              if (last_kb) umma_commit(tfull_t + 8 * buf);  // chunk complete -> the tile's epilogue group may drain it
             }
             __syncwarp();
             if (lane == 0) LM_PROF_ADD(5);
@@ -268,18 +277,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3, half = (warp - EPI_WARP0) >> 2;
+    const int q = warp & 3;
+    const int half = (HALVES == 2) ? ((warp - EPI_WARP0) >> 2) : 0;
+    const uint32_t egroup = (EGROUPS == 2) ? (uint32_t)((warp - EPI_WARP0) >> 2) : 0u;
     const int row = q * 32 + lane, hl = row >> 3, wl = row & 7;  // 16 x 8 patch, 8 pixels per image row
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const size_t plane = (size_t)p.H * p.W * p.Cout;
-    uint32_t buf = 0, bph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t tfull_g = tfull0 + 8 * (egroup * NBUF);
+    uint32_t buf = 0;          // ring slot of the next chunk (all tiles, both groups, advance it)
+    uint32_t phase_bits = 0;   // bit b: parity this group's next wait on slot b expects (its own barrier set)
+    uint32_t tseq = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tseq) {
+      if (EGROUPS == 2 && (tseq & 1u) != egroup) { buf = (buf + (uint32_t)num_chunks) % NBUF; continue; }  // the other group's tile
       const TileCoord t = decode_tile(tile, n_tiles, tiles_x, tiles_img, BN);
       float acc[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) acc[i] = 0.f;
       for (int c = 0; c < num_chunks; ++c) {
-        { LM_PROF_T0(); mbar_wait(tfull0 + 8 * buf, bph); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
+        { LM_PROF_T0(); mbar_wait(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
+        phase_bits ^= 1u << buf;
         tc_fence_after();
         LM_PROF_T0();
         const uint32_t col0 = tmem_base + lane_base + buf * C::ACC_COLS + half * NC;
@@ -308,7 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int i = 0; i < NC; ++i) acc[i] += v[i];
         }
         if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(7);
-        if (++buf == NBUF) { buf = 0; bph ^= 1; }
+        if (++buf == NBUF) buf = 0;
       }
       LM_PROF_T0();
       const int y = t.y0 + hl, x = t.x0 + wl;
@@ -369,47 +384,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           acc[4 * i + 3] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 3] + b.w, 0.f), s.w), h.w);
         }
         if (p.mode == kModeHead) {
-          // 1x1 head (resunet.py:69) over this thread's NC channels, halves combined through smem.
-          float part[MAX_CLASSES];
+          // 1x1 head (resunet.py:69): this thread holds all 64 channels of its pixel (BN = 64 rows are not split).
+          float lg[MAX_CLASSES];
+          float mx = -INFINITY;
 #pragma unroll
           for (int k = 0; k < MAX_CLASSES; ++k) {
-            float s = 0.f;
+            float sdot = 0.f;
             if (k < p.K) {
 #pragma unroll
-              for (int i = 0; i < NC; ++i) s = fmaf(s_head_w[k * 64 + half * NC + i], acc[i], s);
+              for (int i = 0; i < NC; ++i) sdot = fmaf(s_head_w[k * 64 + (half * NC + i) % 64], acc[i], sdot);
             }
-            part[k] = s;
+            lg[k] = (k < p.K) ? sdot + s_head_b[k] : -INFINITY;
+            mx = fmaxf(mx, lg[k]);
           }
-          if (half == 1) {
+          float se = 0.f;
 #pragma unroll
-            for (int k = 0; k < MAX_CLASSES; ++k) s_part[row][k] = part[k];
-          }
-          named_bar_sync(1, NUM_EPI_THREADS);
-          if (half == 0) {
-            float lg[MAX_CLASSES];
-            float mx = -INFINITY;
+          for (int k = 0; k < MAX_CLASSES; ++k) if (k < p.K) se += expf(lg[k] - mx);
+          const float lse = logf(se);
+          int best = 0;
+          float bestv = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < MAX_CLASSES; ++k) {
-              lg[k] = (k < p.K) ? (part[k] + s_part[row][k]) + s_head_b[k] : -INFINITY;
-              mx = fmaxf(mx, lg[k]);
+          for (int k = 0; k < MAX_CLASSES; ++k) {
+            if (k < p.K) {
+              const float sc = (lg[k] - mx) - lse;  // LogSoftmax(dim=1), resunet.py:70
+              if (sc > bestv) { bestv = sc; best = k; }  // first index wins ties (mask.py:185)
+              if (p.scores) p.scores[(((size_t)t.n * p.K + k) * p.H + y) * p.W + x] = sc;
             }
-            float se = 0.f;
-#pragma unroll
-            for (int k = 0; k < MAX_CLASSES; ++k) if (k < p.K) se += expf(lg[k] - mx);
-            const float lse = logf(se);
-            int best = 0;
-            float bestv = -INFINITY;
-#pragma unroll
-            for (int k = 0; k < MAX_CLASSES; ++k) {
-              if (k < p.K) {
-                const float sc = (lg[k] - mx) - lse;  // LogSoftmax(dim=1), resunet.py:70
-                if (sc > bestv) { bestv = sc; best = k; }  // first index wins ties (mask.py:185)
-                if (p.scores) p.scores[(((size_t)t.n * p.K + k) * p.H + y) * p.W + x] = sc;
-              }
-            }
-            p.labels[((size_t)t.n * p.H + y) * p.W + x] = (uint8_t)best;
           }
-          named_bar_sync(1, NUM_EPI_THREADS);
+          p.labels[((size_t)t.n * p.H + y) * p.W + x] = (uint8_t)best;
         } else {
 #pragma unroll
           for (int g = 0; g < NC / 32; ++g) {
