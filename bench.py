@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 
 S_VOL, RES = 300, 256
 GFLOP_PER_SLICE_TC = 96.20 - 0.0755  # all convs minus the 1->64 stem (CUDA cores); K=3
+# mean dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch from the committed ncu --set full capture
+# (profiles/r01_ncu_summary.md, 4 launches of the 37-slice wave); the kernel is tensor/issue bound, DRAM runs at 5-11 % of peak
+TRAFFIC_BYTES_PER_LAUNCH = 399.4e6
 WORKLOAD = "R231 (3-class) 300-slice 256x256 int16 synthetic CT volume per GPU, batch_size=20 (engine waves of 37 slices)"
 
 
@@ -238,7 +241,7 @@ def run_engine(args):
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
                          "kernel": "conv_tc_kernel (tcgen05 kind::tf32, 3 MMAs per k-step => ceiling 1/6 of the bf16 peak)",
                          "launches_timed": int(conv_launches), "avg_launch_ms": conv_ms / max(1, conv_launches),
                          "peak_source": peak_src,
