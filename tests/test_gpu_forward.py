@@ -159,3 +159,12 @@ def test_default_wave_matches_small_waves(engine, models, tmp_path):
     m = _blob(models[3])
     engine.load_weights(0, m.blob, m.n_classes)
     assert np.array_equal(inf.apply(vol), engine.apply_volume(0, vol))
+
+
+def test_sharded_path_equals_whole_volume(engine, models):
+    """lungmask_b200.parallel.apply_sharded (stage-level C-ABI calls + gather) on one rank == lm_apply_volume."""
+    from lungmask_b200.parallel import apply_sharded
+    m = _blob(models[3])
+    engine.load_weights(0, m.blob, m.n_classes)
+    vol = synth.phantom(5, 180, 200, seed=12)
+    assert np.array_equal(apply_sharded(engine, 0, vol, 0, 1), engine.apply_volume(0, vol))

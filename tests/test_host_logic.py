@@ -121,3 +121,18 @@ def test_two_rank_gloo_matches_single_rank():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_lungmask_alias_package_resolves_to_engine_mirror():
+    import importlib
+    for k in [k for k in sys.modules if k == "lungmask" or k.startswith("lungmask.")]:
+        del sys.modules[k]
+    lm = importlib.import_module("lungmask")
+    import lungmask_b200
+    assert lm.LMInferer is lungmask_b200.LMInferer
+    from lungmask.mask import MODEL_URLS, get_model  # noqa: F401
+    from lungmask.utils import bbox_3D, postprocessing, preprocess  # noqa: F401
+    assert set(MODEL_URLS) == {"R231", "LTRCLobes", "R231CovidWeb"} and MODEL_URLS["LTRCLobes"][1] == 6
+    m = np.zeros((10, 10, 10), dtype=np.uint8)
+    m[2:8, 3:7, 4:6] = 1
+    assert tuple(bbox_3D(m, margin=2)) == (0, 10, 1, 9, 2, 8)
