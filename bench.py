@@ -87,8 +87,10 @@ def cpu_port_slices_per_s(sd, vol, n_slices, batch, repeats=1):
     """The oracle port of the reference path on the host cores, on a bounded sample of the workload."""
     import torch
     from oracle import restate
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use the host's cores.  torch's own default is one
+    # thread per physical core (64 on the GPU box: 128 hyper-threads measured 2.7x slower), so restore that.
+    if torch.get_num_threads() == 1 and (os.cpu_count() or 1) > 2:
+        torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     sample = vol[:n_slices]
     best = None
     for _ in range(repeats):
