@@ -28,19 +28,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
   if (threadIdx.x < 64) { sb[threadIdx.x] = bias[threadIdx.x]; ss[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
   const size_t plane = (size_t)H * W;
-  const size_t npix = (size_t)N * plane;
-  // 16 threads per pixel, 4 output channels each; the channel quad of a thread never changes, so its 36 weights
-  // and 12 epilogue constants live in registers for the whole grid-stride loop.
-  const int cq = threadIdx.x & 15;
-  float wr[4][9], br[4], sr[4], hr[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) wr[e][tap] = sw[(cq * 4 + e) * 9 + tap];
-    br[e] = sb[cq * 4 + e]; sr[e] = ss[cq * 4 + e]; hr[e] = sh[cq * 4 + e];
-  }
-  const size_t pix_per_block = blockDim.x >> 4;
-  for (size_t pix = blockIdx.x * pix_per_block + (threadIdx.x >> 4); pix < npix; pix += (size_t)gridDim.x * pix_per_block) {
+  const size_t total = (size_t)N * plane * 16;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(t & 15);
+    const size_t pix = t >> 4;
     const int n = (int)(pix / plane);
     const int r = (int)(pix - (size_t)n * plane);
     const int y = r / W, x = r - y * W;
@@ -62,10 +53,11 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
     float* pl = &lo.x;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
+      const int c = cq * 4 + e;
       float s = 0.f;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) s = fmaf(wr[e][tap], v[tap], s);
-      const float yv = __fadd_rn(__fmul_rn(fmaxf(s + br[e], 0.f), sr[e]), hr[e]);
+      for (int tap = 0; tap < 9; ++tap) s = fmaf(sw[c * 9 + tap], v[tap], s);
+      const float yv = __fadd_rn(__fmul_rn(fmaxf(s + sb[c], 0.f), ss[c]), sh[c]);
       split_tf32(yv, ph[e], pl[e]);
     }
     float* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * 4;
