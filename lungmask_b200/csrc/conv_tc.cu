@@ -225,9 +225,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const bool mine = dual_issue ? ((gc & 1u) == me) : (me == 0u);
         const uint32_t buf = gc % NBUF, bph = (gc / NBUF) & 1;
         const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
-#ifndef LM_UNSAFE_SKIP_TEMPTY
         if (mine) { LM_PROF_T0(); mbar_wait(tempty0 + 8 * buf, bph ^ 1); if (lane == 0) LM_PROF_ADD(2); }
-#endif
         bool first = true;                       // first k-step of the chunk: hi*hi restarts from zero
         const uint32_t corr_acc = c >= NBUF;     // first use of this slot in the tile: corrections restart too
         for (; kb < kend; ++kb) {
