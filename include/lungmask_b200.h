@@ -96,7 +96,9 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
 
 /* Options: "time_convs" (0/1: bracket every tensor-core convolution launch with CUDA events on the engine
  * stream; read the sum with lm_last_conv_timing after an lm_apply_volume* call), "chunk_kb" (k-blocks
- * accumulated inside the tensor core between fp32 round-to-nearest adds; default 1). */
+ * accumulated inside the tensor core between fp32 round-to-nearest adds; sets both layer classes),
+ * "chunk_kb_wide" (the same for the layers with >= 128 output channels only; defaults: 1 for the 64-channel
+ * layers, 2 for the wide ones). */
 LM_API int lm_set_option(lm_engine* e, const char* key, int value);
 LM_API int lm_last_conv_timing(const lm_engine* e, float* conv_ms, int64_t* conv_launches);
 

@@ -152,7 +152,9 @@ struct lm_engine {
   int64_t last_conv_launches = 0;
   float last_ms[7] = {};
   int64_t launches = 0;
-  int chunk_kb = 1;
+  int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
+  int chunk_kb_wide = 2;  // ... for the layers with Cout >= 128 (ring of 2 slots: chunk 1 leaves the tensor pipe waiting
+                          // for the drain; chunk 2 costs < 1e-5 of score accuracy there, tools/debug_gpu.py)
 };
 
 namespace {
@@ -202,7 +204,7 @@ int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_
   for (int i = 0; i < NUM_LAYERS; ++i) {
     ConvParams p = s.params[i];
     p.N = n;
-    p.chunk_kb = e->chunk_kb;
+    p.chunk_kb = (p.Cout >= 128) ? e->chunk_kb_wide : e->chunk_kb;
     if (p.mode == kModeHead) { p.labels = d_labels; p.scores = d_scores; }
     if (time_convs) {
       if (e->ev_used + 2 > e->ev_pool.size()) {
@@ -327,7 +329,8 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   e->device = device;
   e->B = batch_capacity;
   e->num_sms = prop.multiProcessorCount;
-  if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = v; }
+  if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = e->chunk_kb_wide = v; }
+  if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
   CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&e->ev[i]));
   for (int i = 0; i < 2; ++i) CU(cudaEventCreate(&e->ev_conv[i]));
@@ -598,7 +601,8 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!e || !key) return fail(-1, "lm_set_option: NULL argument");
   if (!strcmp(key, "time_convs")) { e->time_convs = value != 0; e->ev_used = 0; return 0; }
   if (!strcmp(key, "post_debug_stage")) { e->post.debug_stage = value; return 0; }
-  if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = value; return 0; }
+  if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = e->chunk_kb_wide = value; return 0; }
+  if (!strcmp(key, "chunk_kb_wide")) { if (value < 1) return fail(-1, "chunk_kb_wide must be >= 1"); e->chunk_kb_wide = value; return 0; }
   return fail(-1, "lm_set_option: unknown key %s", key);
 }
 

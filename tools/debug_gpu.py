@@ -58,11 +58,21 @@ def chunks():
         sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
         ex = restate.unet_forward(torch.as_tensor(restate.normalise(resized)[:, None], dtype=torch.float64), sd64).numpy()
     print("oracle fp32 vs fp64 scores: max %.3e mean %.3e" % (np.abs(want - ex).max(), np.abs(want - ex).mean()))
-    for ck in (4, 2, 1):
-        eng.set_option("chunk_kb", ck)
+    import time
+    for ck, ckw in ((1, 1), (1, 2), (2, 2)):
+        eng.set_option("chunk_kb", ck); eng.set_option("chunk_kb_wide", ckw)
         labels, scores = eng.forward(0, resized, return_scores=True)
-        print("chunk_kb=%d: engine vs fp32 oracle max %.3e mean %.3e | vs fp64 max %.3e mean %.3e | signed mean vs fp64 %.3e" % (
-            ck, np.abs(scores - want).max(), np.abs(scores - want).mean(), np.abs(scores - ex).max(), np.abs(scores - ex).mean(), (scores - ex).mean()), flush=True)
+        print("chunk_kb=%d wide=%d: engine vs fp32 oracle max %.3e mean %.3e | vs fp64 max %.3e mean %.3e" % (
+            ck, ckw, np.abs(scores - want).max(), np.abs(scores - want).mean(), np.abs(scores - ex).max(), np.abs(scores - ex).mean()), flush=True)
+    for K in (3, 6):
+        sdk = synth.random_state_dict(K, seed=10 + K, head_gain=0.3)
+        mk = NativeModel(sdk); eng.load_weights(0, mk.blob, mk.n_classes)
+        vol5 = synth.phantom(5, seed=21); r5, _ = restate.preprocess(vol5, resolution=[256, 256])
+        wl, ws = restate.forward_volume(restate.normalise(r5), sdk, batch_size=2, return_scores=True)
+        for ck, ckw in ((1, 1), (1, 2), (2, 2)):
+            eng.set_option("chunk_kb", ck); eng.set_option("chunk_kb_wide", ckw)
+            l, sc = eng.forward(0, r5, return_scores=True)
+            print("pytest-net K=%d chunk=%d wide=%d: max|dscore| %.3e" % (K, ck, ckw, np.abs(sc - ws).max()), flush=True)
     eng.set_option("chunk_kb", 1)
 
 for f, a in ((chunks, ()),):
