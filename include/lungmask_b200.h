@@ -84,6 +84,10 @@ LM_API int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uin
 LM_API int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
                    int skip_below, uint8_t* out);
 
+/* utils.keep_largest_connected_component(mask), utils.py:390-404: (S,H,W) uint8 0/1 mask -> 0/1 mask of its largest
+ * full-connectivity component (ties: the last in raster order).  Fails (like the reference) on an empty mask. */
+LM_API int lm_keep_largest_component(lm_engine* e, const uint8_t* mask, int S, int H, int W, uint8_t* out);
+
 /* [utils.reshape_mask(mask[i], boxes[i], (H,W)) for i], utils.py:114-129 + mask.py:196-202:
  * (S,mask_h,mask_w) uint8 + boxes -> (S,H,W) uint8. */
 LM_API int lm_reshape_masks(lm_engine* e, const uint8_t* masks, int mask_h, int mask_w, const int32_t* boxes, int S,

@@ -45,6 +45,7 @@ def lib():
         "lm_forward_dev": ([vp, i32, i16p, i32, u8p, C.POINTER(C.c_float)], i32),
         "lm_postprocess": ([vp, u8p, i32, i32, i32, i32p, i32, i32, u8p], i32),
         "lm_reshape_masks": ([vp, u8p, i32, i32, i32p, i32, i32, i32, u8p], i32),
+        "lm_keep_largest_component": ([vp, u8p, i32, i32, i32, u8p], i32),
         "lm_last_timings": ([vp, C.POINTER(C.c_float), C.POINTER(C.c_int64)], i32),
         "lm_set_option": ([vp, C.c_char_p, i32], i32),
         "lm_debug_activation_info": ([i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
@@ -61,6 +62,7 @@ def lib():
 EXPORTS = ["lm_create", "lm_destroy", "lm_last_error", "lm_device", "lm_batch_capacity", "lm_weight_blob_floats",
            "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_preprocess",
            "lm_simple_bodymask", "lm_forward", "lm_forward_dev", "lm_postprocess", "lm_reshape_masks",
+           "lm_keep_largest_component",
            "lm_last_timings", "lm_set_option", "lm_last_conv_timing",
            "lm_debug_activation_info", "lm_debug_read_activation"]
 
@@ -167,6 +169,12 @@ class Engine:
         sp = np.asarray(list(spare), dtype=np.int32)
         out = np.empty(labels.shape, np.uint8)
         _check(lib().lm_postprocess(self._h, _ptr(labels), S, H, W, _ptr(sp) if sp.size else None, int(sp.size), int(skip_below), _ptr(out)))
+        return out
+
+    def keep_largest_component(self, mask):
+        mask = _as(mask, np.uint8, 3)
+        out = np.empty(mask.shape, np.uint8)
+        _check(lib().lm_keep_largest_component(self._h, _ptr(mask), mask.shape[0], mask.shape[1], mask.shape[2], _ptr(out)))
         return out
 
     def reshape_masks(self, masks, boxes, H, W):

@@ -553,6 +553,22 @@ int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, con
   return 0;
 }
 
+int lm_keep_largest_component(lm_engine* e, const uint8_t* mask, int S, int H, int W, uint8_t* out) {
+  if (!e || !mask || !out) return fail(-1, "lm_keep_largest_component: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_keep_largest_component: empty mask");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W;
+  RC(e->d_out.reserve(n));
+  RC(e->d_out2.reserve(n));
+  CU(cudaMemcpyAsync(e->d_out.p, mask, n, cudaMemcpyHostToDevice, e->st));
+  const int r = keep_largest_component_device(e->post, e->d_out.p, S, H, W, e->d_out2.p, e->num_sms, e->st);
+  if (r == -21) return fail(-21, "lm_keep_largest_component: the mask has no foreground (the reference raises IndexError here)");
+  RC(r);
+  CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
 int lm_reshape_masks(lm_engine* e, const uint8_t* masks, int mask_h, int mask_w, const int32_t* boxes, int S, int H,
                      int W, uint8_t* out) {
   if (!e || !masks || !boxes || !out) return fail(-1, "lm_reshape_masks: NULL argument");

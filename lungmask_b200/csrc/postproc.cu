@@ -698,6 +698,43 @@ int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, i
   return (int)cudaGetLastError();
 }
 
+__global__ void select_root_kernel(const uint32_t* __restrict__ parent, uint32_t root, uint8_t* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = (parent[i] != NONE && parent[i] == root) ? 1 : 0;
+}
+__global__ void binarize_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i] ? 1 : 0;
+}
+
+// utils.keep_largest_connected_component (utils.py:390-404): full-connectivity components of a binary mask, the
+// largest one kept (np.argsort(areas)[-1]: among equal areas the highest id, i.e. the last in raster order).
+int keep_largest_component_device(PostScratch& ws, const uint8_t* d_mask, int S, int H, int W, uint8_t* d_out, int num_sms,
+                                  cudaStream_t st) {
+  const size_t n = (size_t)S * H * W;
+  if (n == 0) return 0;
+  if (n >= 0xFFFFFFF0ull) return -20;
+  int rc = ws.reserve(n);
+  if (rc) return rc;
+  const Dim d{S, H, W};
+  const Box full{0, S, 0, H, 0, W};
+  const int g = grid_for(n, 256, num_sms);
+  int64_t launches = 0;
+  binarize_kernel<<<g, 256, 0, st>>>(d_mask, ws.tmp, n);
+  rc = run_ccl<26>(ws.tmp, ws.parent, d, full, num_sms, st, &launches);
+  if (rc) return rc;
+  LM_CUDA(cudaMemsetAsync(ws.area2, 0, n * 4, st));
+  unsigned long long* d_best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.small) + 8192);
+  LM_CUDA(cudaMemsetAsync(d_best, 0, 256 * 8, st));
+  root_area_kernel<<<g, 256, 0, st>>>(ws.parent, ws.area2, n);
+  best_root_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.parent, ws.area2, d_best, n);
+  unsigned long long h_best = 0;
+  LM_CUDA(cudaMemcpyAsync(&h_best, d_best + 1, 8, cudaMemcpyDeviceToHost, st));
+  LM_CUDA(cudaStreamSynchronize(st));
+  if (h_best == 0ull) { LM_CUDA(cudaMemsetAsync(d_out, 0, n, st)); return -21; }  // empty mask: the reference raises (argsort of [])
+  select_root_kernel<<<g, 256, 0, st>>>(ws.parent, (uint32_t)(h_best & 0xFFFFFFFFull), d_out, n);
+  return (int)cudaGetLastError();
+}
+
 int reshape_device(const uint8_t* d_masks, const int32_t* d_boxes, int S, int H, int W, int MH, int MW, uint8_t* d_out,
                    int num_sms, cudaStream_t st) {
   const size_t n = (size_t)S * H * W;

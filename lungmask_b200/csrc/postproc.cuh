@@ -26,6 +26,9 @@ struct PostScratch {
 // utils.postprocessing on a device-resident (S,H,W) uint8 volume -> d_out (S,H,W) uint8.
 int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, int W, const int32_t* spare, int n_spare,
                        int skip_below, uint8_t* d_out, int num_sms, cudaStream_t st, int64_t* launches);
+// utils.keep_largest_connected_component on a device-resident (S,H,W) 0/1 mask; -21 if the mask is empty.
+int keep_largest_component_device(PostScratch& ws, const uint8_t* d_mask, int S, int H, int W, uint8_t* d_out, int num_sms,
+                                  cudaStream_t st);
 // utils.reshape_mask for every slice: (S,MH,MW) masks + (S,4) boxes -> (S,H,W).
 int reshape_device(const uint8_t* d_masks, const int32_t* d_boxes, int S, int H, int W, int MH, int MW, uint8_t* d_out,
                    int num_sms, cudaStream_t st);

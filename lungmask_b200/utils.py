@@ -1,7 +1,7 @@
 """Host-side mirror of the hot-path functions of lungmask/utils.py, backed by the CUDA engine.
 
 Same names and argument meaning as the reference (`preprocess`, `simple_bodymask`, `crop_and_resize`,
-`reshape_mask`, `postprocessing`, `bbox_3D`; lungmask/utils.py:32-129,272-387) so that the reference's
+`reshape_mask`, `postprocessing`, `keep_largest_connected_component`, `bbox_3D`; lungmask/utils.py:32-129,272-404) so that the reference's
 own known-answer tests (tests/test_utils.py:58-107,124-159) run unchanged against them.  Image I/O
 (`read_dicoms`, `load_input_image`) is outside the accelerated path and lives in the CLI module.
 """
@@ -58,6 +58,14 @@ def reshape_mask(mask, tbox, origsize):
 def postprocessing(label_image, spare=[], disable_tqdm=False, skip_below=3):
     """utils.py:272-358 on a (S,H,W) label volume."""
     return _eng().postprocess(np.asarray(label_image), spare=spare, skip_below=skip_below)
+
+
+def keep_largest_connected_component(mask):
+    """utils.py:390-404 -> boolean mask of the largest full-connectivity component (2-D or 3-D input)."""
+    m = (np.asarray(mask) != 0).astype(np.uint8)
+    if m.ndim == 2:
+        return _eng().keep_largest_component(m[None])[0].astype(bool)
+    return _eng().keep_largest_component(m).astype(bool)
 
 
 def bbox_3D(labelmap, margin=2):

@@ -86,3 +86,18 @@ def test_postprocess_non_square(engine):
     lab = synth.label_noise_volume(6, 6, seed=2, speckle=1e-3, H=200, W=312)
     assert np.array_equal(restate.postprocessing(lab), engine.postprocess(lab))
     assert np.array_equal(restate.postprocessing(lab, spare=[6]), engine.postprocess(lab, spare=[6]))
+
+
+def test_keep_largest_component_bit_exact(engine):
+    from lungmask_b200.utils import keep_largest_connected_component
+    rng = np.random.default_rng(3)
+    for shape in ((6, 40, 52), (1, 64, 64), (3, 17, 9)):
+        m = rng.random(shape) < 0.45
+        want = restate.keep_largest_connected_component(m)
+        assert np.array_equal(want, engine.keep_largest_component(m.astype(np.uint8)).astype(bool)), shape
+    m2 = rng.random((33, 47)) < 0.5
+    assert np.array_equal(restate.keep_largest_connected_component(m2), keep_largest_connected_component(m2))
+    two = np.zeros((1, 8, 8), np.uint8)   # two components of equal area: argsort(...)[-1] keeps the later one
+    two[0, 1, 1:4] = 1
+    two[0, 6, 2:5] = 1
+    assert np.array_equal(restate.keep_largest_connected_component(two != 0), engine.keep_largest_component(two).astype(bool))
