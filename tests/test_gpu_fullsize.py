@@ -1,0 +1,74 @@
+"""BASELINE.json's full-size configurations through size-independent properties (the CPU oracle would need
+minutes to hours at these sizes): slice independence of the per-slice stages, run-to-run determinism,
+idempotence of the volume post-processing, label range, and the fusion rule's invariants."""
+import numpy as np
+import pytest
+
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big_engine():
+    from lungmask_b200 import _native
+    eng = _native.Engine(device=0, batch_capacity=37)
+    yield eng
+    eng.close()
+
+
+def _load(eng, slot, K, seed):
+    from lungmask_b200.mask import NativeModel
+    m = NativeModel(synth.random_state_dict(K, seed=seed, head_gain=0.3))
+    eng.load_weights(slot, m.blob, m.n_classes)
+
+
+def test_c3_ltrclobes_512_slices(big_engine):
+    """C3: 6-class model, 512-slice 256x256 volume."""
+    eng = big_engine
+    _load(eng, 0, 6, seed=31)
+    vol = synth.phantom(512, seed=40)
+    raw = eng.apply_volume(0, vol, postprocess=False)
+    assert raw.shape == vol.shape and raw.dtype == np.uint8 and raw.max() <= 5
+    # per-slice stages are independent of how the volume is cut (mask.py:172-187 batches arbitrarily)
+    halves = np.concatenate([eng.apply_volume(0, vol[:200], postprocess=False), eng.apply_volume(0, vol[200:], postprocess=False)])
+    assert np.array_equal(raw, halves)
+    assert np.array_equal(raw, eng.apply_volume(0, vol, postprocess=False))          # deterministic
+    out = eng.apply_volume(0, vol)
+    assert np.array_equal(out, eng.apply_volume(0, vol))
+    assert set(np.unique(out)) <= set(range(6))
+    # utils.postprocessing leaves one hole-free component per label: applying it again changes nothing
+    assert np.array_equal(eng.postprocess(out), out)
+    # every label kept by the post-processing already existed in the raw prediction
+    assert set(np.unique(out)) <= set(np.unique(raw)) | {0}
+
+
+def test_c4_fusion_300_slices(big_engine):
+    """C4: LTRCLobes_R231 fusion on a 300-slice volume (two models, spare-label merge at original resolution)."""
+    eng = big_engine
+    _load(eng, 0, 6, seed=31)
+    _load(eng, 1, 3, seed=32)
+    vol = synth.phantom(300, seed=41)
+    fused = eng.apply_fused(0, 1, vol)
+    assert np.array_equal(fused, eng.apply_fused(0, 1, vol))
+    res_r = eng.apply_volume(1, vol)
+    # mask.py:230: nothing survives where the fill model sees no lung; mask.py:341-342: the spare label never survives
+    assert not np.any(fused[res_r == 0])
+    assert fused.max() <= 5
+    assert np.array_equal(eng.postprocess(fused), fused)
+
+
+def test_c2_r231_300_slices_through_lminferer(tmp_path):
+    """C2 through the public surface: default LMInferer on a 300-slice volume == the capacity-37 engine."""
+    import torch
+    from lungmask_b200 import LMInferer
+    sd = synth.random_state_dict(3, seed=33, head_gain=0.3)
+    p = str(tmp_path / "r231_like.pth")
+    torch.save(sd, p)
+    inf = LMInferer(modelpath=p, tqdm_disable=True)
+    vol = synth.phantom(300, seed=42)
+    out = inf.apply(vol)
+    assert out.shape == vol.shape and out.max() <= 2
+    assert np.array_equal(out, inf.apply(vol))
+    t = inf.engine.last_timings()
+    assert t["kernel_launches"] > 9 * 26
