@@ -233,7 +233,7 @@ def run_engine(args):
         line = {
             "metric": "CT slices/sec @256x256 (R231)", "value": value, "unit": "slices/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3 (fp32-class: tf32 hi/lo split operands, fp32 accumulate)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16x3 (fp32-class: every fp32 value is an fp16 hi + scaled fp16 lo pair, 3 exact products per MAC, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "volumes_per_step_per_gpu": 1, "slices_per_step": world * S_VOL,
                        "l2": "inputs larger than L2: 39 MB volume, ~11.5 GB of activations per 37-slice wave",
@@ -246,7 +246,7 @@ def run_engine(args):
             "clocks": sampler.result(),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
-                         "kernel": "conv_tc_kernel (tcgen05 kind::tf32, 3 MMAs per k-step => ceiling 1/6 of the bf16 peak)",
+                         "kernel": "conv_tc_kernel (tcgen05 kind::f16, 3 products per algorithmic MAC => ceiling 1/3 of the bf16 peak)",
                          "launches_timed": int(conv_launches), "avg_launch_ms": conv_ms / max(1, conv_launches),
                          "peak_source": peak_src,
                          "algorithmic_flops_per_step": GFLOP_PER_SLICE_TC * 1e9 * S_VOL},

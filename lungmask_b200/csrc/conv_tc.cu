@@ -47,12 +47,20 @@ __device__ unsigned long long g_conv_prof[16];
 #define LM_PROF_T0()
 #define LM_PROF_ADD(slot)
 #endif
+// LM_EXP: bit mask of timing-only ablations for tools/conv_probe (results are wrong with any bit set):
+//   1 no correction MMAs, 2 chunk drains skip their TMEM loads, 4 tile epilogue skips staging + TMA stores,
+//   8 single MMA issuer, 16 no wide MMAs (only the N = BN correction MMAs), 32 producer loads no weights after the first ring fill
+#ifndef LM_EXP
+#define LM_EXP 0
+#endif
 namespace {
 
-constexpr int BM = 128, BK = 32, TILE_H = 16, TILE_W = 8;
+constexpr int BM = 128, BK = kBK, TILE_H = 16, TILE_W = 8;  // BK channels = one 128-byte row (64 fp16 / 32 tf32)
+constexpr int ROW_BYTES = 128;
 constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
-constexpr int A_PLANE_BYTES_3x3 = HALO_W * HALO_H * BK * 4;  // 180 rows x 128 B = 23040 B per plane
-constexpr int A_PLANE_BYTES_1x1 = BM * BK * 4;               // 16 KB per plane
+constexpr int A_PLANE_BYTES_3x3 = HALO_W * HALO_H * ROW_BYTES;  // 180 rows x 128 B = 23040 B per plane
+constexpr int A_PLANE_BYTES_1x1 = BM * ROW_BYTES;               // 16 KB per plane
+constexpr int F32_ROW_CH = 32;                                  // channels per staged 128-byte row of an fp32 output
 constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB (both planes), 1024-aligned
 constexpr int NUM_A_BUFS = 2;
 constexpr int OUT_STAGE_BYTES = BM * 128;  // output staging: 8 epilogue warps x 4 KB (32 pixels x 32 channels fp32), x2 halves
@@ -63,7 +71,7 @@ constexpr int MAX_CLASSES = 8;
 
 template <int BN>
 struct Cfg {
-  static constexpr int B_PLANE_BYTES = BN * BK * 4;
+  static constexpr int B_PLANE_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * B_PLANE_BYTES;      // one weight tile (hi + lo planes) per k-block
   static constexpr int STAGES = (BN == 64) ? 6 : 3;
   static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
@@ -134,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // barrier phases of the k-blocks it skips, so it must never skip as many phases as a ring is deep
   // (weight ring: chunk_kb <= STAGES-1; activation ring: every channel block must contain k-blocks of both
   // issuers, i.e. 9 taps and chunk_kb < 9).  Otherwise warp 1 issues everything.
-  const bool dual_issue = (taps == 9) && (chunk_kb <= STAGES - 1);
+  const bool dual_issue = (taps == 9) && (chunk_kb <= STAGES - 1) && !(LM_EXP & 8);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -182,8 +190,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int tap = 0; tap < taps; ++tap) {
           { LM_PROF_T0(); mbar_wait(empty0 + 8 * s, ph ^ 1); if (lane == 0) LM_PROF_ADD(1); }
           if (elect_one()) {
-            mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
-            tma_load_4d(smem_u32(smem_b) + s * C::STAGE_BYTES, &tmB, full0 + 8 * s, c, t.n0, tap, 0);
+            if ((LM_EXP & 32) && (tile != (int)blockIdx.x || cb > 0 || tap >= STAGES)) {
+              mbar_arrive(full0 + 8 * s);  // ablation: reuse whatever the stage holds
+            } else {
+              mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
+              tma_load_4d(smem_u32(smem_b) + s * C::STAGE_BYTES, &tmB, full0 + 8 * s, c, t.n0, tap, 0);
+            }
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -199,7 +211,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // lives in accumulator slot g % NBUF and NBUF is even, so each slot is only ever written by one issuer
     // and the order of additions into every accumulator is fixed: results stay bit-deterministic.
     const uint32_t me = (warp == 3) ? 1u : 0u;
+#if LM_OPERAND_F16
+    const uint32_t idesc_wide = make_idesc_f16(BM, 2 * BN), idesc_corr = make_idesc_f16(BM, BN);
+#define LM_UMMA_C umma_f16_c
+#define LM_UMMA umma_f16
+#else
     const uint32_t idesc_wide = make_idesc_tf32(BM, 2 * BN), idesc_corr = make_idesc_tf32(BM, BN);
+#define LM_UMMA_C umma_tf32_c
+#define LM_UMMA umma_tf32
+#endif
     // shared-memory descriptors as (lo, hi) words: lo = start>>4 | LBO, hi = SBO | version | swizzle.
     // A: K-major SW128 entered at an arbitrary 128-byte row, 8-row group stride = one patch row.
     const uint32_t desc_hi_a = (uint32_t)((patch_w * 128) >> 4) | (1u << 14) | (2u << 29);
@@ -238,17 +258,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const bool last_kb = (kb == kend - 1);
             if (elect_one()) {
               if (first) {
-                umma_tf32_c<false>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_corr);                                          // hi*hi := (zero init)
-                umma_tf32(d_tmem + BN, hi_a | alo, hi_b | (b_lo + (uint32_t)(C::B_PLANE_BYTES >> 4)), idesc_corr, corr_acc);  // hi*lo
+                LM_UMMA_C<false>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_corr);                                          // hi*hi := (zero init)
+                LM_UMMA(d_tmem + BN, hi_a | alo, hi_b | (b_lo + (uint32_t)(C::B_PLANE_BYTES >> 4)), idesc_corr, corr_acc);  // hi*lo
               } else {
-                umma_tf32_c<true>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_wide);                                           // [hi*hi | hi*lo] +=
+                if (!(LM_EXP & 16)) LM_UMMA_C<true>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_wide);                       // [hi*hi | hi*lo] +=
               }
-              umma_tf32_c<true>(d_tmem + BN, hi_a | (alo + a_lo_plane), hi_b | b_lo, idesc_corr);                         // lo*hi
+              if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + a_lo_plane), hi_b | b_lo, idesc_corr);      // lo*hi
 #pragma unroll
-              for (int k = 1; k < BK / 8; ++k) {
-                const uint32_t ko = (uint32_t)(k * 2);  // 8 tf32 = 32 B along K, >>4
-                umma_tf32_c<true>(d_tmem, hi_a | (alo + ko), hi_b | (b_lo + ko), idesc_wide);
-                umma_tf32_c<true>(d_tmem + BN, hi_a | (alo + a_lo_plane + ko), hi_b | (b_lo + ko), idesc_corr);
+              for (int k = 1; k < ROW_BYTES / 32; ++k) {
+                const uint32_t ko = (uint32_t)(k * 2);  // one MMA k-step = 32 B along K (16 fp16 / 8 tf32), >>4
+                if (!(LM_EXP & 16)) LM_UMMA_C<true>(d_tmem, hi_a | (alo + ko), hi_b | (b_lo + ko), idesc_wide);
+                if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + a_lo_plane + ko), hi_b | (b_lo + ko), idesc_corr);
               }
               umma_commit(empty0 + 8 * s);                  // weight stage consumed (only this issuer read it)
               if (last_tap) umma_commit(aempty0 + 8 * ab);  // this issuer is done with the activation buffer
@@ -303,7 +323,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
         float v[NC];
 #pragma unroll
-        for (int j = 0; j < NC / 32; ++j) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
+        for (int j = 0; j < NC / 32; ++j) {
+          if (!(LM_EXP & 2) || last_use) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
+        }
         if (last_use) {
           float w[NC];
 #pragma unroll
@@ -313,7 +335,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
 #pragma unroll
-          for (int i = 0; i < NC; ++i) acc[i] = (acc[i] + v[i]) + w[i];
+          for (int i = 0; i < NC; ++i) acc[i] = (acc[i] + v[i]) + w[i] * kLoUnscale;  // exact power-of-two rescale of hi*lo + lo*hi
         } else {
           tmem_ld_wait();
           tc_fence_before();
@@ -338,14 +360,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t stage = smem_u32(smem_out) + (uint32_t)(warp - EPI_WARP0) * 4096u;
       const bool issuer = (lane == 0);
       const int ty0 = t.y0 + 4 * q;  // first image row of this warp's 32 pixels
-      auto stage_row = [&](uint32_t r, const float* v8x4) {  // 32 floats -> row r, chunk j at (j ^ (r & 7))
+      auto stage_row = [&](uint32_t r, const uint32_t* v8x4) {  // 32 words (128 B) -> row r, chunk j at (j ^ (r & 7))
+        if (LM_EXP & 4) {  // keep the values alive, skip the shared-memory traffic
+          uint32_t x = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x ^= v8x4[j];
+          if (x == 0x12345u) p.labels[0] = 1;
+          return;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t addr = stage + r * 128u + (uint32_t)((j ^ (int)(r & 7u)) << 4);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v8x4[4 * j]), "f"(v8x4[4 * j + 1]),
-                       "f"(v8x4[4 * j + 2]), "f"(v8x4[4 * j + 3])
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v8x4[4 * j]), "r"(v8x4[4 * j + 1]),
+                       "r"(v8x4[4 * j + 2]), "r"(v8x4[4 * j + 3])
                        : "memory");
         }
+      };
+      // one 128-byte row of operand-format channels (BK of them) of plane `plane`, from fp32 values
+      auto pack_row = [&](const float* src, int plane, uint32_t* v) {
+#if LM_OPERAND_F16
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          __half h0, l0, h1, l1;
+          split_f16(src[2 * i], h0, l0);
+          split_f16(src[2 * i + 1], h1, l1);
+          v[i] = plane ? pack_half2(l0, l1) : pack_half2(h0, h1);
+        }
+#else
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float hi, lo;
+          split_tf32(src[i], hi, lo);
+          v[i] = __float_as_uint(plane ? lo : hi);
+        }
+#endif
       };
       auto round_begin = [&]() {
         if (issuer) tma_store_wait_read();  // this warp's previous store has finished reading the buffer
@@ -358,18 +406,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
       if (p.mode == kModeLinear) {
 #pragma unroll
-        for (int g = 0; g < NC / 32; ++g) {
-          float v[32];
+        for (int g = 0; g < NC / F32_ROW_CH; ++g) {
+          uint32_t v[32];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(bias4 + g * 8 + i);
-            v[4 * i] = acc[g * 32 + 4 * i] + b.x; v[4 * i + 1] = acc[g * 32 + 4 * i + 1] + b.y;
-            v[4 * i + 2] = acc[g * 32 + 4 * i + 2] + b.z; v[4 * i + 3] = acc[g * 32 + 4 * i + 3] + b.w;
+            v[4 * i] = __float_as_uint(acc[g * 32 + 4 * i] + b.x); v[4 * i + 1] = __float_as_uint(acc[g * 32 + 4 * i + 1] + b.y);
+            v[4 * i + 2] = __float_as_uint(acc[g * 32 + 4 * i + 2] + b.z); v[4 * i + 3] = __float_as_uint(acc[g * 32 + 4 * i + 3] + b.w);
           }
           round_begin();
           stage_row((uint32_t)lane, v);
           round_end();
-          if (issuer) { tma_store_4d(&tmOut, stage, cbase + g * 32, t.x0, ty0, t.n); tma_store_commit(); }
+          if (issuer && !(LM_EXP & 4)) { tma_store_4d(&tmOut, stage, cbase + g * F32_ROW_CH, t.x0, ty0, t.n); tma_store_commit(); }
         }
       } else {
         const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cbase);
@@ -413,21 +461,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           p.labels[((size_t)t.n * p.H + y) * p.W + x] = (uint8_t)best;
         } else {
+#if LM_OPERAND_F16
+          {  // fp16 saturates: report instead of storing inf
+            bool ovf = false;
 #pragma unroll
-          for (int g = 0; g < NC / 32; ++g) {
+            for (int i = 0; i < NC; ++i) ovf |= !(fabsf(acc[i]) <= kOpMax);
+            if (__any_sync(0xffffffffu, ovf) && lane == 0 && p.range_flag) *p.range_flag = 1;
+          }
+#endif
+#pragma unroll
+          for (int g = 0; g < NC / BK; ++g) {
 #pragma unroll
             for (int plane = 0; plane < 2; ++plane) {
-              float v[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float hi, lo;
-                split_tf32(acc[g * 32 + i], hi, lo);
-                v[i] = plane ? lo : hi;
-              }
+              uint32_t v[32];
+              pack_row(acc + g * BK, plane, v);
               round_begin();
               stage_row((uint32_t)lane, v);
               round_end();
-              if (issuer) { tma_store_5d(&tmOut, stage, cbase + g * 32, t.x0, ty0, plane, t.n); tma_store_commit(); }
+              if (issuer && !(LM_EXP & 4)) { tma_store_5d(&tmOut, stage, cbase + g * BK, t.x0, ty0, plane, t.n); tma_store_commit(); }
             }
           }
           if (p.mode == kModeReluBnPool) {
@@ -436,27 +487,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const bool writer = (lane & 9) == 0;
             const uint32_t prow = (uint32_t)((lane >> 4) * (TILE_W / 2) + ((lane & 7) >> 1));
 #pragma unroll
-            for (int g = 0; g < NC / 32; ++g) {
-              float pv[32];
+            for (int g = 0; g < NC / BK; ++g) {
+              float pv[BK];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float s = acc[g * 32 + i] + __shfl_xor_sync(0xffffffffu, acc[g * 32 + i], 1);
+              for (int i = 0; i < BK; ++i) {
+                float s = acc[g * BK + i] + __shfl_xor_sync(0xffffffffu, acc[g * BK + i], 1);
                 s = s + __shfl_xor_sync(0xffffffffu, s, 8);
                 pv[i] = s * 0.25f;
               }
 #pragma unroll
               for (int plane = 0; plane < 2; ++plane) {
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  float hi, lo;
-                  split_tf32(pv[i], hi, lo);
-                  v[i] = plane ? lo : hi;
-                }
+                uint32_t v[32];
+                pack_row(pv, plane, v);
                 round_begin();
                 if (writer) stage_row(prow, v);
                 round_end();
-                if (issuer) { tma_store_5d(&tmPool, stage, cbase + g * 32, t.x0 >> 1, ty0 >> 1, plane, t.n); tma_store_commit(); }
+                if (issuer && !(LM_EXP & 4)) { tma_store_5d(&tmPool, stage, cbase + g * BK, t.x0 >> 1, ty0 >> 1, plane, t.n); tma_store_commit(); }
               }
             }
           }
@@ -493,30 +539,38 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box) {
+#if LM_OPERAND_F16
+constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#else
+constexpr CUtensorMapDataType kOpType = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+#endif
+
+int encode(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const cuuint64_t* dims,
+           const cuuint64_t* strides, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                   es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-int make_act_map(CUtensorMap* m, const float* base, int n_cap, int H, int W, int Cch, int taps) {
+int make_act_map(CUtensorMap* m, const void* base, int n_cap, int H, int W, int Cch, int taps) {
+  const cuuint64_t E = kOpBytes;
   cuuint64_t dims[5] = {(cuuint64_t)Cch, (cuuint64_t)W, (cuuint64_t)H, 2, (cuuint64_t)n_cap};
-  cuuint64_t strides[4] = {(cuuint64_t)Cch * 4, (cuuint64_t)W * Cch * 4, (cuuint64_t)H * W * Cch * 4,
-                           (cuuint64_t)2 * H * W * Cch * 4};
+  cuuint64_t strides[4] = {(cuuint64_t)Cch * E, (cuuint64_t)W * Cch * E, (cuuint64_t)H * W * Cch * E,
+                           (cuuint64_t)2 * H * W * Cch * E};
   const cuuint32_t halo = taps == 9 ? 2 : 0;
   cuuint32_t box[5] = {BK, TILE_W + halo, TILE_H + halo, 2, 1};
-  return encode(m, base, 5, dims, strides, box);
+  return encode(m, kOpType, base, 5, dims, strides, box);
 }
 
 }  // namespace
 
-int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const float* weights,
+int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const void* weights,
                    const ConvParams& p, int n_capacity) {
+  const cuuint64_t E = kOpBytes;
   if (p.H % TILE_H || p.W % TILE_W || p.C0 % BK || p.C1 % BK || (p.taps != 1 && p.taps != 9)) return -2;
   const int BN = conv_tile_n(p.Cout);
   if (p.Cout % BN) return -3;
@@ -528,16 +582,16 @@ int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const f
   // TMA-store maps: one epilogue warp's rows per store
   if (p.mode == kModeReluBn || p.mode == kModeReluBnPool) {
     cuuint64_t od[5] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, 2, (cuuint64_t)n_capacity};
-    cuuint64_t os[4] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4,
-                        (cuuint64_t)2 * p.H * p.W * p.Cout * 4};
-    cuuint32_t ob[5] = {BK, TILE_W, 4, 1, 1};  // one epilogue warp: 32 channels x 8 x 4 pixels of one plane
-    r = encode(&maps->out, p.out, 5, od, os, ob);
+    cuuint64_t os[4] = {(cuuint64_t)p.Cout * E, (cuuint64_t)p.W * p.Cout * E, (cuuint64_t)p.H * p.W * p.Cout * E,
+                        (cuuint64_t)2 * p.H * p.W * p.Cout * E};
+    cuuint32_t ob[5] = {BK, TILE_W, 4, 1, 1};  // one epilogue warp: BK channels (128 B) x 8 x 4 pixels of one plane
+    r = encode(&maps->out, kOpType, p.out, 5, od, os, ob);
     if (r) return r;
   } else if (p.mode == kModeLinear) {
     cuuint64_t od[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)n_capacity};
     cuuint64_t os[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.W * p.Cout * 4, (cuuint64_t)p.H * p.W * p.Cout * 4};
-    cuuint32_t ob[4] = {BK, TILE_W, 4, 1};
-    r = encode(&maps->out, p.out, 4, od, os, ob);
+    cuuint32_t ob[4] = {F32_ROW_CH, TILE_W, 4, 1};
+    r = encode(&maps->out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.out, 4, od, os, ob);
     if (r) return r;
   } else {
     maps->out = maps->a0;
@@ -545,19 +599,19 @@ int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const f
   if (p.mode == kModeReluBnPool) {
     const int Hp = p.H / 2, Wp = p.W / 2;
     cuuint64_t od[5] = {(cuuint64_t)p.Cout, (cuuint64_t)Wp, (cuuint64_t)Hp, 2, (cuuint64_t)n_capacity};
-    cuuint64_t os[4] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)Wp * p.Cout * 4, (cuuint64_t)Hp * Wp * p.Cout * 4,
-                        (cuuint64_t)2 * Hp * Wp * p.Cout * 4};
+    cuuint64_t os[4] = {(cuuint64_t)p.Cout * E, (cuuint64_t)Wp * p.Cout * E, (cuuint64_t)Hp * Wp * p.Cout * E,
+                        (cuuint64_t)2 * Hp * Wp * p.Cout * E};
     cuuint32_t ob[5] = {BK, TILE_W / 2, 2, 1, 1};
-    r = encode(&maps->pool, p.out_pool, 5, od, os, ob);
+    r = encode(&maps->pool, kOpType, p.out_pool, 5, od, os, ob);
     if (r) return r;
   } else {
     maps->pool = maps->a0;
   }
   const int Cin = p.C0 + p.C1;
   cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)p.Cout, (cuuint64_t)p.taps, 2};
-  cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)p.Cout * Cin * 4, (cuuint64_t)p.taps * p.Cout * Cin * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * E, (cuuint64_t)p.Cout * Cin * E, (cuuint64_t)p.taps * p.Cout * Cin * E};
   cuuint32_t box[4] = {BK, (cuuint32_t)BN, 1, 2};
-  return encode(&maps->b, weights, 4, dims, strides, box);
+  return encode(&maps->b, kOpType, weights, 4, dims, strides, box);
 }
 
 template <int BN>

@@ -1,14 +1,40 @@
 // Host-visible description of one tensor-core convolution launch (see conv_tc.cu).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Operand format of the tensor-core convolutions (compile-time, one format per build):
+//   1 (default)  fp16 pairs, tcgen05 kind::f16:  x = hi + lo * 2^-11, hi = fp16(x), lo = fp16((x - hi) * 2^11).
+//                Both halves carry 11 significant bits (as tf32 does), every product is exact in fp32, and an
+//                MMA instruction covers K = 16 at the rate kind::tf32 covers K = 8: the 3-product scheme runs
+//                at twice the tf32 rate and moves half the bytes.  The scaled low half keeps the residuals
+//                of small values out of the fp16 subnormal range; the hi*lo + lo*hi accumulator is multiplied
+//                by 2^-11 when it is read.  fp16 saturates at 65504: the epilogues raise ConvParams::range_flag
+//                when a value leaves that range and the engine reports an error instead of a wrong mask.
+//   0            tf32 pairs, kind::tf32 (round 1's first scheme; no range limit, half the throughput).
+#ifndef LM_OPERAND_F16
+#define LM_OPERAND_F16 1
+#endif
+
 namespace lm {
 
+#if LM_OPERAND_F16
+using op_t = __half;
+constexpr float kLoScale = 2048.f, kLoUnscale = 1.f / 2048.f;
+constexpr float kOpMax = 65504.f;
+#else
+using op_t = float;
+constexpr float kLoScale = 1.f, kLoUnscale = 1.f;
+constexpr float kOpMax = 3.0e38f;
+#endif
+constexpr int kOpBytes = (int)sizeof(op_t);
+constexpr int kBK = 128 / kOpBytes;  // input channels per k-block: one 128-byte swizzle row (64 fp16 / 32 tf32)
+
 // Activation tensors feeding / produced by the tensor-core convolutions are "split planes":
-//   [N][2][H][W][C] fp32, plane 0 = tf32-rounded value (hi), plane 1 = tf32-rounded residual (lo),
-// so that hi + lo reproduces the fp32 value to ~2^-22 and both planes are exact kind::tf32 operands.
+//   [N][2][H][W][C] op_t, plane 0 = hi, plane 1 = lo (scaled by kLoScale), so that hi + lo * kLoUnscale
+// reproduces the fp32 value to ~2^-22 and both planes are exact tensor-core operands.
 // Weights are [2][taps][Cout][Cin] with the same hi / lo split.
 
 enum ConvMode : int {
@@ -24,13 +50,14 @@ struct ConvParams {
   int Cout;
   int taps;           // 9 (3x3, pad 1) or 1 (1x1)
   int mode;           // ConvMode
-  int chunk_kb;       // k-blocks (32 channels x 1 tap) accumulated inside the tensor core before the
+  int chunk_kb;       // k-blocks (kBK channels x 1 tap) accumulated inside the tensor core before the
                       // partial sum is added, round-to-nearest, into fp32 registers
   const float* bias;  // [Cout]
   const float* scale; // [Cout]  folded BN:  y = relu(.) * scale + shift
   const float* shift; // [Cout]
-  float* out;         // mode 0/1: [N][2][H][W][Cout]; mode 2: [N][H][W][Cout]; mode 3: unused
-  float* out_pool;    // mode 1: [N][2][H/2][W/2][Cout]
+  void* out;          // mode 0/1: op_t [N][2][H][W][Cout]; mode 2: fp32 [N][H][W][Cout]; mode 3: unused
+  void* out_pool;     // mode 1: op_t [N][2][H/2][W/2][Cout]
+  int* range_flag;    // set to 1 when an output leaves the operand format's range (fp16 build); may be nullptr
   const float* head_w;  // mode 3: [K][Cout]
   const float* head_b;  // mode 3: [K]
   int K;                // mode 3: classes (<= 8)
@@ -45,7 +72,7 @@ struct ConvMaps {
 };
 
 // Builds the TMA descriptors. src1 may be nullptr when C1 == 0. Returns 0 on success.
-int make_conv_maps(ConvMaps* maps, const float* src0, const float* src1, const float* weights,
+int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const void* weights,
                    const ConvParams& p, int n_capacity);
 
 // Launches the convolution on `stream`. Returns a cudaError_t value (0 = ok).

@@ -114,7 +114,7 @@ struct UpSpec { int after_layer, src, dst; };
 const UpSpec UPS[4] = {{9, L0, U0}, {12, L1, U1}, {15, L2, U2}, {18, L3, U3}};
 
 struct LayerWeights {
-  float* w = nullptr;  // [2][taps][Cout][Cin] split
+  void* w = nullptr;  // op_t [2][taps][Cout][Cin] split
   float* bias = nullptr;
   float* scale = nullptr;
   float* shift = nullptr;
@@ -135,7 +135,9 @@ using namespace lm_impl;
 struct lm_engine {
   int device = 0, B = 0, num_sms = 0;
   cudaStream_t st = nullptr;
-  float* act[NUM_ACT] = {};
+  void* act[NUM_ACT] = {};  // split buffers: op_t planes; "L" buffers: fp32
+  int* d_range = nullptr;   // device flag: a value left the operand format's range (fp16 build: |x| > 65504)
+  int* h_range = nullptr;   // pinned host copy, refreshed at the end of every forward
   Slot slots[LM_MAX_SLOTS];
   DevBuf<int16_t> d_vol, d_resized;
   DevBuf<int32_t> d_boxes;
@@ -198,13 +200,14 @@ int upload(float** dst, const float* src, size_t n, cudaStream_t st) {
 
 int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_t* d_labels, float* d_scores,
                   bool time_convs) {
-  RC(launch_stem(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R, e->num_sms, e->st));
+  RC(launch_stem(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R, e->d_range, e->num_sms, e->st));
   e->launches++;
   int up = 0;
   for (int i = 0; i < NUM_LAYERS; ++i) {
     ConvParams p = s.params[i];
     p.N = n;
     p.chunk_kb = (p.Cout >= 128) ? e->chunk_kb_wide : e->chunk_kb;
+    p.range_flag = e->d_range;
     if (p.mode == kModeHead) { p.labels = d_labels; p.scores = d_scores; }
     if (time_convs) {
       if (e->ev_used + 2 > e->ev_pool.size()) {
@@ -217,7 +220,8 @@ int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_
     e->launches++;
     if (up < 4 && UPS[up].after_layer == i) {
       const ActSpec& src = ACT[UPS[up].src];
-      RC(launch_upsample2x(e->act[UPS[up].src], e->act[UPS[up].dst], n, R >> src.level, R >> src.level, src.C, e->num_sms, e->st));
+      RC(launch_upsample2x(static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n, R >> src.level, R >> src.level, src.C,
+                           e->d_range, e->num_sms, e->st));
       e->launches++;
       ++up;
     }
@@ -257,6 +261,7 @@ int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t
       CU(cudaStreamSynchronize(e->st));
     }
   }
+  CU(cudaMemcpyAsync(e->h_range, e->d_range, sizeof(int), cudaMemcpyDeviceToHost, e->st));  // read by check_range after the caller's sync
   if (conv_ms) {  // device time of the tensor-core convolution launches alone (CUDA events on the launch stream)
     CU(cudaStreamSynchronize(e->st));
     RC(drain_conv_events(e));
@@ -288,6 +293,17 @@ int inference_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, in
   RC(reshape_device(masks, e->d_boxes.p, S, H, W, R, R, d_out, e->num_sms, e->st));
   e->launches++;
   CU(cudaEventRecord(e->ev[5], e->st));
+  return 0;
+}
+
+// After a stream synchronisation: did any activation leave the operand format's range during the forward passes?
+int check_range(lm_engine* e) {
+  if (*e->h_range) {
+    *e->h_range = 0;
+    cudaMemsetAsync(e->d_range, 0, sizeof(int), e->st);
+    return fail(-40, "an activation exceeded the fp16 operand range (|x| > 65504); the result is invalid "
+                     "(rebuild with -DLM_OPERAND_F16=0 for the tf32 operand format)");
+  }
   return 0;
 }
 
@@ -336,9 +352,13 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   for (int i = 0; i < 2; ++i) CU(cudaEventCreate(&e->ev_conv[i]));
   for (int a = 0; a < NUM_ACT; ++a) {
     const int hw = R >> ACT[a].level;
-    const size_t elems = (size_t)batch_capacity * hw * hw * ACT[a].C * (ACT[a].split ? 2 : 1);
-    CU(cudaMalloc(&e->act[a], elems * sizeof(float)));
+    const size_t elems = (size_t)batch_capacity * hw * hw * ACT[a].C;
+    CU(cudaMalloc(&e->act[a], ACT[a].split ? elems * 2 * sizeof(op_t) : elems * sizeof(float)));
   }
+  CU(cudaMalloc(&e->d_range, sizeof(int)));
+  CU(cudaMemset(e->d_range, 0, sizeof(int)));
+  CU(cudaMallocHost(&e->h_range, sizeof(int)));
+  *e->h_range = 0;
   RC(e->d_scratch.reserve(64));
   *out = e;
   return 0;
@@ -349,6 +369,8 @@ void lm_destroy(lm_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
   for (int a = 0; a < NUM_ACT; ++a) cudaFree(e->act[a]);
+  cudaFree(e->d_range);
+  cudaFreeHost(e->h_range);
   for (auto& s : e->slots) {
     cudaFree(s.stem_w); cudaFree(s.stem_bias); cudaFree(s.stem_scale); cudaFree(s.stem_shift); cudaFree(s.head_w); cudaFree(s.head_b);
     for (auto& l : s.lw) { cudaFree(l.w); cudaFree(l.bias); cudaFree(l.scale); cudaFree(l.shift); }
@@ -387,8 +409,8 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
     const int Cin = L.C0 + L.C1;
     const size_t nw = (size_t)L.Cout * Cin * L.taps;
     CU(cudaMemcpyAsync(d_tmp, q, nw * sizeof(float), cudaMemcpyHostToDevice, e->st)); q += nw;
-    if (!s.lw[i].w) CU(cudaMalloc(&s.lw[i].w, 2 * nw * sizeof(float)));
-    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->st));
+    if (!s.lw[i].w) CU(cudaMalloc(&s.lw[i].w, 2 * nw * sizeof(op_t)));
+    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->d_range, e->st));
     CU(cudaStreamSynchronize(e->st));
     RC(upload(&s.lw[i].bias, q, L.Cout, e->st)); q += L.Cout;
     if (has_bn) {
@@ -408,6 +430,13 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   RC(upload(&s.head_b, q, K, e->st)); q += K;
   cudaFree(d_tmp);
   if ((size_t)(q - blob) != n_floats) return fail(-1, "lm_load_weights: internal blob walk mismatch");
+  CU(cudaMemcpyAsync(e->h_range, e->d_range, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  if (*e->h_range) {
+    *e->h_range = 0;
+    CU(cudaMemsetAsync(e->d_range, 0, sizeof(int), e->st));
+    return fail(-40, "lm_load_weights: a convolution weight exceeds the fp16 operand range (|w| > 65504)");
+  }
   for (int i = 0; i < NUM_LAYERS; ++i) {
     const LayerSpec& L = LAYERS[i];
     ConvParams p{};
@@ -435,7 +464,7 @@ int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int
   CU(cudaEventRecord(e->ev[6], e->st));
   CU(cudaStreamSynchronize(e->st));
   collect_timings(e);
-  return 0;
+  return check_range(e);
 }
 
 int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
@@ -453,7 +482,7 @@ int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, in
   CU(cudaEventRecord(e->ev[6], e->st));
   CU(cudaStreamSynchronize(e->st));
   collect_timings(e);
-  return 0;
+  return check_range(e);
 }
 
 int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out) {
@@ -478,7 +507,7 @@ int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vo
   CU(cudaEventRecord(e->ev[6], e->st));
   CU(cudaStreamSynchronize(e->st));
   collect_timings(e);
-  return 0;
+  return check_range(e);
 }
 
 int lm_preprocess(lm_engine* e, const int16_t* vol, int S, int H, int W, int out_h, int out_w, int clip,
@@ -525,7 +554,7 @@ int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uint8_t* l
   RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, scores, nullptr));
   CU(cudaMemcpyAsync(labels, e->d_labels.p, nr, cudaMemcpyDeviceToHost, e->st));
   CU(cudaStreamSynchronize(e->st));
-  return 0;
+  return check_range(e);
 }
 
 int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* conv_ms) {
@@ -534,7 +563,7 @@ int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint
   e->launches = 0;
   RC(forward_all(e, slot, d_resized, S, d_labels, nullptr, conv_ms));
   CU(cudaStreamSynchronize(e->st));
-  return 0;
+  return check_range(e);
 }
 
 int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
@@ -606,10 +635,11 @@ int lm_debug_read_activation(lm_engine* e, int act_id, int n, float* out) {
     CU(cudaMemcpy(out, e->act[act_id], (size_t)n * per * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
   }
-  std::vector<float> tmp((size_t)n * 2 * per);
-  CU(cudaMemcpy(tmp.data(), e->act[act_id], tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<op_t> tmp((size_t)n * 2 * per);
+  CU(cudaMemcpy(tmp.data(), e->act[act_id], tmp.size() * sizeof(op_t), cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; ++i)
-    for (size_t k = 0; k < per; ++k) out[(size_t)i * per + k] = tmp[((size_t)i * 2) * per + k] + tmp[((size_t)i * 2 + 1) * per + k];
+    for (size_t k = 0; k < per; ++k)
+      out[(size_t)i * per + k] = (float)tmp[((size_t)i * 2) * per + k] + (float)tmp[((size_t)i * 2 + 1) * per + k] * kLoUnscale;
   return 0;
 }
 

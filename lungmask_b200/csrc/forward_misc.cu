@@ -3,22 +3,49 @@
 //                      (resunet.py:93-97 for down_path.0.block.0/2): K = 9, no tensor-core shape.
 //   * upsample2x_kernel  nn.Upsample(mode='bilinear', scale_factor=2) (resunet.py:132), applied AFTER the
 //                      1x1 convolution (the two commute: both are linear and the bilinear weights sum
-//                      to 1), writing the tf32 hi/lo split planes the next convolution consumes.
-//   * prep_conv_weights  OIHW fp32 -> [2][tap][Cout][Cin] tf32 hi/lo planes (one-time, at weight load).
-// All are HBM-bound streaming kernels: 16 threads per pixel x 4 channels each so that every warp store
-// instruction writes two fully coalesced 256-byte runs.
+//                      to 1), writing the hi/lo split planes the next convolution consumes.
+//   * prep_conv_weights  OIHW fp32 -> [2][tap][Cout][Cin] hi/lo operand planes (one-time, at weight load).
+// All are HBM-bound streaming kernels: each thread produces 16 bytes of each plane (CPT = 8 fp16 / 4 tf32
+// channels) so that every warp store instruction writes fully coalesced 128-byte runs.
 #include "forward_misc.cuh"
 #include "sm100_ptx.cuh"
 
 namespace lm {
 namespace {
 
-__global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ in, float* __restrict__ out,
+constexpr int CPT = 16 / kOpBytes;  // channels per thread
+
+// CPT fp32 values -> 16 bytes of the hi plane and 16 bytes of the lo plane; flags values outside the format's range
+__device__ __forceinline__ void split_store(const float* v, op_t* hi_dst, op_t* lo_dst, bool& ovf) {
+  uint4 h, l;
+#if LM_OPERAND_F16
+  uint32_t* ph = &h.x;
+  uint32_t* pl = &l.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __half h0, l0, h1, l1;
+    split_f16(v[2 * e], h0, l0);
+    split_f16(v[2 * e + 1], h1, l1);
+    ph[e] = pack_half2(h0, h1);
+    pl[e] = pack_half2(l0, l1);
+    ovf |= !(fabsf(v[2 * e]) <= kOpMax) | !(fabsf(v[2 * e + 1]) <= kOpMax);
+  }
+#else
+  float* ph = reinterpret_cast<float*>(&h.x);
+  float* pl = reinterpret_cast<float*>(&l.x);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_tf32(v[e], ph[e], pl[e]);
+#endif
+  *reinterpret_cast<uint4*>(hi_dst) = h;
+  *reinterpret_cast<uint4*>(lo_dst) = l;
+}
+
+__global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ in, op_t* __restrict__ out,
                                                    const float* __restrict__ w,      // [64][9]
                                                    const float* __restrict__ bias,   // [64]
                                                    const float* __restrict__ scale,  // [64]
                                                    const float* __restrict__ shift,  // [64]
-                                                   int N, int H, int W) {
+                                                   int N, int H, int W, int* __restrict__ range_flag) {
   __shared__ float sw[64 * 9], sb[64], ss[64], sh[64];
   // (hu + 1024) / 1624 for every HU value the pre-processing can produce ([-1024, 600]): float64 division, then
   // the cast to fp32 (mask.py:168,178-182), tabulated once per block instead of nine fp64 divisions per thread
@@ -28,10 +55,12 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
   if (threadIdx.x < 64) { sb[threadIdx.x] = bias[threadIdx.x]; ss[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
   const size_t plane = (size_t)H * W;
-  const size_t total = (size_t)N * plane * 16;
+  constexpr int TPP = 64 / CPT;  // threads per pixel
+  const size_t total = (size_t)N * plane * TPP;
+  bool ovf = false;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(t & 15);
-    const size_t pix = t >> 4;
+    const int cq = (int)(t % TPP);
+    const size_t pix = t / TPP;
     const int n = (int)(pix / plane);
     const int r = (int)(pix - (size_t)n * plane);
     const int y = r / W, x = r - y * W;
@@ -48,29 +77,27 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
       }
       v[tap] = val;
     }
-    float4 hi, lo;
-    float* ph = &hi.x;
-    float* pl = &lo.x;
+    float yv[CPT];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = cq * 4 + e;
+    for (int e = 0; e < CPT; ++e) {
+      const int c = cq * CPT + e;
       float s = 0.f;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) s = fmaf(sw[c * 9 + tap], v[tap], s);
-      const float yv = __fadd_rn(__fmul_rn(fmaxf(s + sb[c], 0.f), ss[c]), sh[c]);
-      split_tf32(yv, ph[e], pl[e]);
+      yv[e] = __fadd_rn(__fmul_rn(fmaxf(s + sb[c], 0.f), ss[c]), sh[c]);
     }
-    float* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * 4;
-    *reinterpret_cast<float4*>(o) = hi;
-    *reinterpret_cast<float4*>(o + plane * 64) = lo;
+    op_t* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * CPT;
+    split_store(yv, o, o + plane * 64, ovf);
   }
+  if (ovf && range_flag) *range_flag = 1;
 }
 
 // in: [N][h][w][C] fp32 -> out: [N][2][2h][2w][C] split planes. PyTorch semantics (align_corners=False):
 // src = max(0.5*(dst+0.5)-0.5, 0), i0 = (int)src, i1 = i0 + (i0 < size-1), l1 = src - i0, l0 = 1 - l1.
-__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                         int N, int h, int w, int C) {
-  const int cq_per_pix = C >> 2;
+__global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, op_t* __restrict__ out,
+                                                         int N, int h, int w, int C, int* __restrict__ range_flag) {
+  const int cq_per_pix = C / CPT;
+  bool ovf = false;
   const int H = 2 * h, W = 2 * w;
   const size_t oplane = (size_t)H * W;
   const size_t total = (size_t)N * oplane * cq_per_pix;
@@ -84,32 +111,36 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
     const int y0 = (int)sy, x0 = (int)sx;
     const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
     const float ly1 = sy - (float)y0, ly0 = 1.f - ly1, lx1 = sx - (float)x0, lx0 = 1.f - lx1;
-    const float* base = in + (size_t)n * h * w * C + cq * 4;
-    const float4 p00 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x0) * C));
-    const float4 p01 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x1) * C));
-    const float4 p10 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x0) * C));
-    const float4 p11 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x1) * C));
-    float4 hi, lo;
-#define LM_BILERP(f)                                                                                     \
-  {                                                                                                      \
-    const float vv = ly0 * (lx0 * p00.f + lx1 * p01.f) + ly1 * (lx0 * p10.f + lx1 * p11.f);              \
-    split_tf32(vv, hi.f, lo.f);                                                                          \
-  }
-    LM_BILERP(x) LM_BILERP(y) LM_BILERP(z) LM_BILERP(w)
+    const float* base = in + (size_t)n * h * w * C + cq * CPT;
+    float vv[CPT];
+#pragma unroll
+    for (int q = 0; q < CPT / 4; ++q) {
+      const float4 p00 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x0) * C) + q);
+      const float4 p01 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x1) * C) + q);
+      const float4 p10 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x0) * C) + q);
+      const float4 p11 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x1) * C) + q);
+#define LM_BILERP(f, e) vv[4 * q + e] = ly0 * (lx0 * p00.f + lx1 * p01.f) + ly1 * (lx0 * p10.f + lx1 * p11.f);
+      LM_BILERP(x, 0) LM_BILERP(y, 1) LM_BILERP(z, 2) LM_BILERP(w, 3)
 #undef LM_BILERP
-    float* o = out + ((size_t)n * 2 * oplane + r) * C + cq * 4;
-    *reinterpret_cast<float4*>(o) = hi;
-    *reinterpret_cast<float4*>(o + oplane * C) = lo;
+    }
+    op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
+    split_store(vv, o, o + oplane * C, ovf);
   }
+  if (ovf && range_flag) *range_flag = 1;
 }
 
-__global__ void prep_conv_weights_kernel(const float* __restrict__ oihw, float* __restrict__ out, int Cout, int Cin,
-                                         int taps) {
+__global__ void prep_conv_weights_kernel(const float* __restrict__ oihw, op_t* __restrict__ out, int Cout, int Cin,
+                                         int taps, int* __restrict__ range_flag) {
   const size_t total = (size_t)Cout * Cin * taps;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t tap = i % taps, ci = (i / taps) % Cin, co = i / ((size_t)taps * Cin);
-    float hi, lo;
+    op_t hi, lo;
+#if LM_OPERAND_F16
+    split_f16(oihw[i], hi, lo);
+    if (!(fabsf(oihw[i]) <= kOpMax) && range_flag) *range_flag = 1;
+#else
     split_tf32(oihw[i], hi, lo);
+#endif
     const size_t o = (tap * Cout + co) * Cin + ci;
     out[o] = hi;
     out[total + o] = lo;
@@ -124,23 +155,23 @@ inline int grid_for(size_t total, int block, int num_sms) {
 
 }  // namespace
 
-int launch_stem(const int16_t* in, float* out, const float* w, const float* bias, const float* scale,
-                const float* shift, int N, int H, int W, int num_sms, cudaStream_t stream) {
-  const size_t total = (size_t)N * H * W * 16;
-  stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, w, bias, scale, shift, N, H, W);
+int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
+                const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream) {
+  const size_t total = (size_t)N * H * W * (64 / CPT);
+  stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag);
   return (int)cudaGetLastError();
 }
 
-int launch_upsample2x(const float* in, float* out, int N, int h, int w, int C, int num_sms, cudaStream_t stream) {
-  const size_t total = (size_t)N * 4 * h * w * (C / 4);
-  upsample2x_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, out, N, h, w, C);
+int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream) {
+  const size_t total = (size_t)N * 4 * h * w * (C / CPT);
+  upsample2x_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag);
   return (int)cudaGetLastError();
 }
 
-int launch_prep_conv_weights(const float* oihw, float* out, int Cout, int Cin, int taps, cudaStream_t stream) {
+int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, cudaStream_t stream) {
   const size_t total = (size_t)Cout * Cin * taps;
   prep_conv_weights_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, stream>>>(
-      oihw, out, Cout, Cin, taps);
+      oihw, static_cast<op_t*>(out), Cout, Cin, taps, range_flag);
   return (int)cudaGetLastError();
 }
 

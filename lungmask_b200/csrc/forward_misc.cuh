@@ -2,13 +2,15 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "conv_tc.cuh"  // op_t: the operand format of the split planes
 
 namespace lm {
 // resized HU slices int16 [N][H][W] -> split planes [N][2][H][W][64]
-int launch_stem(const int16_t* in, float* out, const float* w, const float* bias, const float* scale,
-                const float* shift, int N, int H, int W, int num_sms, cudaStream_t stream);
+// (range_flag: device int set to 1 when a value leaves the operand format's range; may be nullptr)
+int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
+                const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream);
 // fp32 [N][h][w][C] -> split planes [N][2][2h][2w][C]
-int launch_upsample2x(const float* in, float* out, int N, int h, int w, int C, int num_sms, cudaStream_t stream);
-// OIHW fp32 -> [2][taps][Cout][Cin] tf32 hi/lo
-int launch_prep_conv_weights(const float* oihw, float* out, int Cout, int Cin, int taps, cudaStream_t stream);
+int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream);
+// OIHW fp32 -> [2][taps][Cout][Cin] hi/lo operand planes
+int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, cudaStream_t stream);
 }  // namespace lm

@@ -2,6 +2,7 @@
 // Hand-written for this repo; no CUTLASS dependency.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -180,6 +181,27 @@ __device__ __forceinline__ void umma_tf32_c(uint32_t d_tmem, uint64_t a_desc, ui
                  : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16 operands), fp32 accumulate; accumulate flag fixed at compile time.
+template <bool ACC>
+__device__ __forceinline__ void umma_f16_c(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  if (ACC)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+                 : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B (32 fp32), 8-row swizzle atoms 1024 B apart.
 // Field layout follows the sm_100 shared-memory matrix descriptor (start>>4 | LBO | SBO | version=1
 // | layout type 2 = SWIZZLE_128B).
@@ -196,6 +218,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with fp16 A/B (format 0), D=f32, A/B K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns.
@@ -225,6 +252,16 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   float r = x - hi;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
   lo = __uint_as_float(l);
+}
+
+// fp32 -> (fp16 hi, fp16 lo * 2^11): hi + lo * 2^-11 == x to ~2^-22 (x - hi is exact in fp32; the scaled
+// residual keeps 11 significant bits even where x - hi would be an fp16 subnormal).  |x| must be <= 65504.
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * 2048.f);
+}
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
 }  // namespace lm

@@ -41,11 +41,22 @@ __host__ __device__ inline float tf32_rna(float x) {
   memcpy(&x, &u, 4);
   return x;
 }
-struct Split { float hi, lo; };
-__host__ __device__ inline Split split(float x) { Split s; s.hi = tf32_rna(x); s.lo = tf32_rna(x - s.hi); return s; }
+// operand-format split (conv_tc.cuh): value = hi + lo * kLoUnscale
+struct Split { op_t hi, lo; };
+__host__ __device__ inline Split split(float x) {
+  Split s;
+#if LM_OPERAND_F16
+  s.hi = __float2half_rn(x);
+  s.lo = __float2half_rn((x - __half2float(s.hi)) * 2048.f);
+#else
+  s.hi = tf32_rna(x); s.lo = tf32_rna(x - s.hi);
+#endif
+  return s;
+}
+__host__ __device__ inline double joined(const Split& s) { return (double)(float)s.hi + (double)(float)s.lo * (double)kLoUnscale; }
 
 // activation [N][2][H][W][C]; logical value index = ((n*H+y)*W+x)*C+c
-__global__ void fill_act(float* base, int N, int H, int W, int C, uint32_t seed, bool ints) {
+__global__ void fill_act(op_t* base, int N, int H, int W, int C, uint32_t seed, bool ints) {
   const size_t total = (size_t)N * H * W * C, plane = (size_t)H * W * C;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = i / plane, r = i - n * plane;
@@ -55,7 +66,7 @@ __global__ void fill_act(float* base, int N, int H, int W, int C, uint32_t seed,
   }
 }
 // weights [2][taps][Cout][Cin]; logical OIHW index = ((co*Cin+ci)*taps+tap)
-__global__ void fill_w(float* base, int Cout, int Cin, int taps, uint32_t seed, float wscale, bool ints) {
+__global__ void fill_w(op_t* base, int Cout, int Cin, int taps, uint32_t seed, float wscale, bool ints) {
   const size_t total = (size_t)Cout * Cin * taps;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t tap = i % taps, ci = (i / taps) % Cin, co = i / ((size_t)taps * Cin);
@@ -74,15 +85,18 @@ struct Layer {
 static double h_act(uint32_t seed, int H, int W, int C, int n, int y, int x, int c, bool ints) {
   if (y < 0 || y >= H || x < 0 || x >= W) return 0.0;
   const Split s = split(gen(seed, (((uint64_t)n * H + y) * W + x) * C + c, ints));
-  return (double)s.hi + (double)s.lo;
+  return joined(s);
 }
 static double h_w(uint32_t seed, int Cin, int taps, int co, int ci, int tap, float wscale, bool ints) {
   const Split s = split(gen(seed, ((uint64_t)co * Cin + ci) * taps + tap, ints) * (ints ? 1.f : wscale));
-  return (double)s.hi + (double)s.lo;
+  return joined(s);
 }
 
 struct Bufs {
-  float *src0 = nullptr, *src1 = nullptr, *w = nullptr, *out = nullptr, *pool = nullptr, *bias, *scale, *shift, *hw, *hb, *scores = nullptr;
+  op_t *src0 = nullptr, *src1 = nullptr, *w = nullptr;
+  void *out = nullptr, *pool = nullptr;
+  float *bias, *scale, *shift, *hw, *hb, *scores = nullptr;
+  int* range_flag = nullptr;
   uint8_t* labels = nullptr;
 };
 
@@ -97,13 +111,15 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   const float wscale = 1.0f / sqrtf((float)Cin * L.taps) * 1.7f;
   Bufs b;
   const size_t plane = (size_t)L.H * L.W;
-  CK(cudaMalloc(&b.src0, (size_t)N * 2 * plane * L.C0 * 4));
-  if (L.C1) CK(cudaMalloc(&b.src1, (size_t)N * 2 * plane * L.C1 * 4));
-  CK(cudaMalloc(&b.w, (size_t)2 * L.taps * L.Cout * Cin * 4));
+  CK(cudaMalloc(&b.src0, (size_t)N * 2 * plane * L.C0 * sizeof(op_t)));
+  if (L.C1) CK(cudaMalloc(&b.src1, (size_t)N * 2 * plane * L.C1 * sizeof(op_t)));
+  CK(cudaMalloc(&b.w, (size_t)2 * L.taps * L.Cout * Cin * sizeof(op_t)));
   const size_t out_elems = (size_t)N * plane * L.Cout * (L.mode == kModeLinear ? 1 : 2);
-  CK(cudaMalloc(&b.out, out_elems * 4));
-  CK(cudaMemset(b.out, 0xFF, out_elems * 4));
-  if (L.mode == kModeReluBnPool) { CK(cudaMalloc(&b.pool, out_elems)); CK(cudaMemset(b.pool, 0xFF, out_elems)); }
+  const size_t out_esize = L.mode == kModeLinear ? 4 : sizeof(op_t);
+  CK(cudaMalloc(&b.out, out_elems * out_esize));
+  CK(cudaMemset(b.out, 0xFF, out_elems * out_esize));
+  if (L.mode == kModeReluBnPool) { CK(cudaMalloc(&b.pool, out_elems / 4 * sizeof(op_t))); CK(cudaMemset(b.pool, 0xFF, out_elems / 4 * sizeof(op_t))); }
+  CK(cudaMalloc(&b.range_flag, 4)); CK(cudaMemset(b.range_flag, 0, 4));
   CK(cudaMalloc(&b.bias, L.Cout * 4)); CK(cudaMalloc(&b.scale, L.Cout * 4)); CK(cudaMalloc(&b.shift, L.Cout * 4));
   std::vector<float> hb(L.Cout), hs(L.Cout), hh(L.Cout), hhw(8 * 64), hhb(8);
   for (int c = 0; c < L.Cout; ++c) { hb[c] = h_param(11, c, 0, ints); hs[c] = h_param(11, c, 1, ints); hh[c] = h_param(11, c, 2, ints); }
@@ -127,7 +143,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   ConvParams p{};
   p.N = N; p.H = L.H; p.W = L.W; p.C0 = L.C0; p.C1 = L.C1; p.Cout = L.Cout; p.taps = L.taps; p.mode = L.mode;
   p.chunk_kb = chunk_kb; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
-  p.head_w = b.hw; p.head_b = b.hb; p.K = L.K; p.labels = b.labels; p.scores = b.scores;
+  p.head_w = b.hw; p.head_b = b.hb; p.K = L.K; p.labels = b.labels; p.scores = b.scores; p.range_flag = b.range_flag;
   ConvMaps maps;
   int r = make_conv_maps(&maps, b.src0, b.src1, b.w, p, N);
   if (r) { printf("make_conv_maps failed %d\n", r); exit(2); }
@@ -150,9 +166,13 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   const double flops = 2.0 * N * plane * L.Cout * Cin * L.taps;
 
   if (check) {
-    std::vector<float> ho(out_elems), hp;
-    CK(cudaMemcpy(ho.data(), b.out, out_elems * 4, cudaMemcpyDeviceToHost));
-    if (b.pool) { hp.resize(out_elems / 4); CK(cudaMemcpy(hp.data(), b.pool, out_elems, cudaMemcpyDeviceToHost)); }
+    std::vector<float> ho;       // mode 2: fp32 output
+    std::vector<op_t> hs_, hp;   // split-plane outputs
+    if (L.mode == kModeLinear) { ho.resize(out_elems); CK(cudaMemcpy(ho.data(), b.out, out_elems * 4, cudaMemcpyDeviceToHost)); }
+    else { hs_.resize(out_elems); CK(cudaMemcpy(hs_.data(), b.out, out_elems * sizeof(op_t), cudaMemcpyDeviceToHost)); }
+    if (b.pool) { hp.resize(out_elems / 4); CK(cudaMemcpy(hp.data(), b.pool, out_elems / 4 * sizeof(op_t), cudaMemcpyDeviceToHost)); }
+    int hflag = 0; CK(cudaMemcpy(&hflag, b.range_flag, 4, cudaMemcpyDeviceToHost));
+    if (hflag) printf("range_flag set!\n");
     std::vector<uint8_t> hl; std::vector<float> hsco;
     if (L.mode == kModeHead) {
       hl.resize((size_t)N * plane); CK(cudaMemcpy(hl.data(), b.labels, hl.size(), cudaMemcpyDeviceToHost));
@@ -202,7 +222,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
         if (L.mode == kModeLinear) got = ho[pi * L.Cout + co];
         else {
           const size_t o = ((size_t)n * 2 * plane + (size_t)y * L.W + x) * L.Cout + co;
-          got = (double)ho[o] + (double)ho[o + plane * L.Cout];
+          got = (double)(float)hs_[o] + (double)(float)hs_[o + plane * L.Cout] * (double)kLoUnscale;
         }
         const double err = fabs(got - yv[co]);
         max_err = std::max(max_err, err); max_ref = std::max(max_ref, fabs(yv[co]));
@@ -220,7 +240,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
         for (int co = 0; co < L.Cout; ++co) {
           const double ref = 0.25 * (y4[0][co] + y4[1][co] + y4[2][co] + y4[3][co]);
           const size_t o = ((size_t)n * 2 * Hp * Wp + (size_t)yy * Wp + xx) * L.Cout + co;
-          const double got = (double)hp[o] + (double)hp[o + (size_t)Hp * Wp * L.Cout];
+          const double got = (double)(float)hp[o] + (double)(float)hp[o + (size_t)Hp * Wp * L.Cout] * (double)kLoUnscale;
           max_pool_err = std::max(max_pool_err, fabs(got - ref));
         }
       }
@@ -236,7 +256,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
     unsigned long long pr[16]; conv_prof_read(pr);
     const int BNt = conv_tile_n(L.Cout);
     const double tiles = (double)N * (L.H / 16) * (L.W / 8) * (L.Cout / BNt) * reps;
-    const double kbs = tiles * (Cin / 32) * L.taps;
+    const double kbs = tiles * (Cin / kBK) * L.taps;
     const double ctas = std::min<double>(num_sms, tiles / reps) * reps;
     printf("PROF  %-18s per k-block cycles: kernel %.0f | producer wait aempty %.0f bempty %.0f | mma wait tempty %.0f afull %.0f bfull %.0f issue %.0f | epi wait tfull %.0f drain %.0f, tile-epilogue per tile %.0f\n",
            L.name, pr[9] / kbs * 1.0 * 1, pr[0] / kbs, pr[1] / kbs, pr[2] / kbs, pr[3] / kbs, pr[4] / kbs, pr[5] / kbs, pr[6] / kbs, pr[7] / kbs, pr[8] / tiles);
@@ -247,7 +267,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
     printf("TIME  %-22s N=%d %3dx%-3d C=%4d+%-4d->%4d taps=%d: %.3f ms  %.1f TFLOP/s(algorithmic)\n", L.name, N, L.H, L.W,
            L.C0, L.C1, L.Cout, L.taps, ms, flops / ms * 1e-9);
   cudaFree(b.src0); cudaFree(b.src1); cudaFree(b.w); cudaFree(b.out); cudaFree(b.pool); cudaFree(b.bias); cudaFree(b.scale);
-  cudaFree(b.shift); cudaFree(b.hw); cudaFree(b.hb); cudaFree(b.labels); cudaFree(b.scores);
+  cudaFree(b.shift); cudaFree(b.hw); cudaFree(b.hb); cudaFree(b.labels); cudaFree(b.scores); cudaFree(b.range_flag);
   return ms;
 }
 
@@ -261,9 +281,9 @@ int main(int argc, char** argv) {
   printf("device %s SMs %d; batch %d chunk_kb %d\n", prop.name, sms, batch, chunk);
   if (!timing_only) {
     const Layer small[] = {
-        {"ints 1tile", 16, 8, 32, 0, 64, 9, kModeReluBn, 0},
+        {"ints 1tile", 16, 8, kBK, 0, 64, 9, kModeReluBn, 0},
         {"ints 128->128", 16, 32, 128, 0, 128, 9, kModeReluBn, 0},
-        {"ints concat", 16, 16, 32, 32, 64, 9, kModeReluBn, 0},
+        {"ints concat", 16, 16, kBK, kBK, 64, 9, kModeReluBn, 0},
         {"ints 1x1", 16, 8, 64, 0, 128, 1, kModeLinear, 0},
     };
     for (const Layer& L : small) run_layer(L, 2, chunk, sms, true, true, 0);
