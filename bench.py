@@ -239,6 +239,7 @@ def run_engine(args):
                        "l2": "inputs larger than L2: 39 MB volume, ~11.5 GB of activations per 37-slice wave",
                        "weights": "seeded synthetic state_dict, 60 Adam steps on phantoms (released .pth needs network)",
                        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+                       "mma_issuers_per_cta": 2 if os.environ.get("LM_DUAL_ISSUE", "0") not in ("", "0") else 1,
                        "e2e_matches_device_path": same},
             "e2e": {"value": e2e_value, "unit": "slices/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(vol.nbytes), "d2h_bytes_per_step": int(vol.size)},

@@ -102,6 +102,135 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int n_tiles, int tile
   return t;
 }
 
+#if LM_OPERAND_F16
+#define LM_UMMA_C umma_f16_c
+#define LM_UMMA umma_f16
+#define LM_MAKE_IDESC make_idesc_f16
+#else
+#define LM_UMMA_C umma_tf32_c
+#define LM_UMMA umma_tf32
+#define LM_MAKE_IDESC make_idesc_tf32
+#endif
+
+struct IssueArgs {
+  uint32_t me;     // issuer 0 / 1
+  int first_tile, total_tiles, tile_step, num_cb, chunk_kb;
+  uint32_t tmem_base, smem_a, smem_b;
+  uint32_t full0, empty0, tfull0, tempty0, afull0, aempty0;  // mbarrier arrays (shared-memory addresses)
+};
+
+// The MMA issue loop of one issuer thread.  Chunk g (counted over all tiles of the CTA) lives in accumulator slot
+// g % NBUF and, with two issuers (DUAL), belongs to issuer g & 1; NBUF is even, so every slot is written by one
+// issuer only and the order of additions into each accumulator is fixed (bit-deterministic results).  With DUAL
+// both issuers wait on EVERY weight-stage and activation-buffer barrier in order (a wait that has already
+// completed costs a few instructions) so that their phase bits can never alias; only the owner of a k-block issues
+// its MMAs and releases its weight stage, both release every activation buffer (barrier count 2).
+//
+// Software pipelining: the tensor pipe's instruction queue is only a few MMAs deep, so the gap between the last MMA
+// of one k-block and the first MMA of the next must stay short.  The barrier waits and ring bookkeeping of k-block
+// i+1 (weight stage, activation buffer) are therefore executed in the MIDDLE of k-block i's MMA burst and the
+// burst's remaining MMAs then follow back to back with k-block i+1's first ones.
+template <int BN, int TAPS, bool DUAL>
+__device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
+  using C = Cfg<BN>;
+  constexpr uint32_t STAGES = C::STAGES, NBUF = C::NBUF;
+  constexpr int EGROUPS = C::EGROUPS;
+  constexpr int PATCH_W = (TAPS == 9) ? HALO_W : TILE_W;  // shared-memory rows per image row of the patch
+  constexpr uint32_t A_PLANE = (uint32_t)((TAPS == 9) ? A_PLANE_BYTES_3x3 : A_PLANE_BYTES_1x1) >> 4;
+  constexpr uint32_t B_PLANE = (uint32_t)C::B_PLANE_BYTES >> 4;
+  constexpr uint32_t idesc_wide = LM_MAKE_IDESC(BM, 2 * BN), idesc_corr = LM_MAKE_IDESC(BM, BN);
+  // shared-memory descriptors as (lo, hi) words: lo = start>>4 | LBO, hi = SBO | version | swizzle.
+  // A: K-major SW128 entered at an arbitrary 128-byte row, 8-row group stride = one patch row.
+  constexpr uint64_t hi_a = (uint64_t)((uint32_t)((PATCH_W * 128) >> 4) | (1u << 14) | (2u << 29)) << 32;
+  constexpr uint64_t hi_b = (uint64_t)((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29)) << 32;
+  const uint32_t a_base_lo = ((g.smem_a & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t b_base_lo = ((g.smem_b & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t me = g.me;
+  const int num_kb = g.num_cb * TAPS, chunk_kb = g.chunk_kb;
+  if (g.first_tile >= g.total_tiles) return;
+
+  // state of the k-block whose barriers have been waited for ("current")
+  uint32_t s = 0, ph = 0, ab = 0, aph = 0;  // weight ring / activation ring position and phase
+  uint32_t gc = 0;                          // chunks closed by this CTA so far -> slot gc % NBUF, owner gc & 1
+  uint32_t tseq = 0;                        // tiles processed: the epilogue group (BN = 64) of a tile is tseq & 1
+  int kc = 0;                               // k-blocks already in the open chunk
+  int kb_left = num_kb;                     // k-blocks of the tile still to issue (including the current one)
+  uint32_t cit = 0;                         // chunks of this tile already closed
+  auto is_mine = [&](uint32_t chunk) { return !DUAL || ((chunk & 1u) == me); };
+  // waits of the first k-block
+  mbar_wait(g.afull0, 0);
+  if (is_mine(0)) mbar_wait(g.tempty0, 1);
+  mbar_wait(g.full0, 0);
+
+  for (int tile = g.first_tile; tile < g.total_tiles; tile += g.tile_step) {
+    const bool last_tile = tile + g.tile_step >= g.total_tiles;
+    for (int cb = 0; cb < g.num_cb; ++cb) {
+      const uint32_t a_cb = a_base_lo + ab * (uint32_t)(A_BUF_BYTES >> 4);
+      const uint32_t ab_cur = ab;
+      const bool last_cb = (cb == g.num_cb - 1);
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+        // tap (dy, dx) = the same patch entered (dy * PATCH_W + dx) rows further (16-byte units: 8 per row)
+        const uint32_t tap_off = (TAPS == 9) ? (uint32_t)(((tap / 3) * PATCH_W + (tap % 3)) * 8) : 0u;
+        const bool mine = is_mine(gc);
+        const uint32_t buf = gc % NBUF;
+        const uint32_t d_tmem = g.tmem_base + buf * (uint32_t)C::ACC_COLS;
+        const uint32_t alo = a_cb + tap_off;
+        const uint32_t blo = b_base_lo + s * (uint32_t)(C::STAGE_BYTES >> 4);
+        const bool first = (kc == 0);
+        const uint32_t s_cur = s;
+        // ---- first part of the burst
+        if (mine) {
+          tc_fence_after();
+          if (first) {
+            // first k-step of a chunk: hi*hi restarts from zero; the corrections restart only at the slot's first
+            // chunk of the tile (cit < NBUF), so the two halves need separate instructions here
+            LM_UMMA_C<false>(d_tmem, hi_a | alo, hi_b | blo, idesc_corr);                              // hi*hi :=
+            LM_UMMA(d_tmem + BN, hi_a | alo, hi_b | (blo + B_PLANE), idesc_corr, cit >= NBUF ? 1u : 0u);  // hi*lo
+          } else {
+            LM_UMMA_C<true>(d_tmem, hi_a | alo, hi_b | blo, idesc_wide);                               // [hi*hi | hi*lo] +=
+          }
+          if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + A_PLANE), hi_b | blo, idesc_corr);  // lo*hi
+          LM_UMMA_C<true>(d_tmem, hi_a | (alo + 2u), hi_b | (blo + 2u), idesc_wide);
+          if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + A_PLANE + 2u), hi_b | (blo + 2u), idesc_corr);
+        }
+        // ---- close the bookkeeping of this k-block, advance to the next one and wait for its barriers
+        --kb_left;
+        const bool chunk_end = (++kc == chunk_kb) || (kb_left == 0);
+        const uint32_t tfull_cur = g.tfull0 + 8 * ((EGROUPS == 2 ? (tseq & 1u) : 0u) * NBUF + buf);
+        if (chunk_end) { kc = 0; ++gc; ++cit; }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        bool has_next = true;
+        if (tap == TAPS - 1) {  // the next k-block opens a channel block (possibly of the next tile)
+          if (++ab == (uint32_t)NUM_A_BUFS) { ab = 0; aph ^= 1u; }
+          if (last_cb) {
+            has_next = !last_tile;
+            kb_left = num_kb; cit = 0; ++tseq;   // (kc is 0 here: a tile's last k-block closes its chunk)
+          }
+          if (has_next) mbar_wait(g.afull0 + 8 * ab, aph);
+        }
+        if (has_next) mbar_wait(g.full0 + 8 * s, ph);
+        // ---- rest of the burst, then the releases
+        if (mine) {
+#pragma unroll
+          for (int k = 2; k < ROW_BYTES / 32; ++k) {
+            const uint32_t ko = (uint32_t)(k * 2);  // one MMA k-step = 32 B along K (16 fp16 / 8 tf32), >>4
+            LM_UMMA_C<true>(d_tmem, hi_a | (alo + ko), hi_b | (blo + ko), idesc_wide);
+            if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + A_PLANE + ko), hi_b | (blo + ko), idesc_corr);
+          }
+          umma_commit(g.empty0 + 8 * s_cur);           // weight stage consumed (only this issuer read it)
+          if (chunk_end) umma_commit(tfull_cur);       // chunk complete -> the tile's epilogue group may drain it
+        }
+        if (tap == TAPS - 1) umma_commit(g.aempty0 + 8 * ab_cur);  // arrives once this issuer's MMAs on the buffer have retired
+        // the accumulator slot of the next chunk is awaited LAST: with a two-slot ring it is the one hand-shake that
+        // regularly blocks (the epilogue drains chunk i-1 while chunk i executes), and blocking in the middle of the
+        // burst would leave the tensor pipe with half a k-block queued (measured: 8 % slower on the BN = 128 layers)
+        if (has_next && kc == 0 && is_mine(gc)) mbar_wait(g.tempty0 + 8 * (gc % NBUF), (((gc / NBUF) & 1u) ^ 1u));
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -135,14 +264,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int num_kb = num_cb * taps;
   const int a_plane_bytes = taps == 9 ? A_PLANE_BYTES_3x3 : A_PLANE_BYTES_1x1;
   const int halo = taps == 9 ? 1 : 0;
-  const int patch_w = TILE_W + 2 * halo;  // shared-memory rows per image row of the patch
   const int chunk_kb = p.chunk_kb;
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
-  // Two MMA-issuing warps take alternate chunks when that is provably safe: an issuer does not observe the
-  // barrier phases of the k-blocks it skips, so it must never skip as many phases as a ring is deep
-  // (weight ring: chunk_kb <= STAGES-1; activation ring: every channel block must contain k-blocks of both
-  // issuers, i.e. 9 taps and chunk_kb < 9).  Otherwise warp 1 issues everything.
-  const bool dual_issue = (taps == 9) && (chunk_kb <= STAGES - 1) && !(LM_EXP & 8);
+  // Two MMA-issuing warps take alternate chunks unless a chunk spans a whole weight ring (then the issuer that
+  // does not own it could fall a full ring behind and its phase bit would alias); see mma_issue_loop.
+  const bool dual_issue = p.dual_issue && (chunk_kb <= STAGES - 1) && (num_chunks >= 2);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -203,98 +329,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1 || warp == 3) {
-    // ------------------------------------------------------------------ MMA issuers (two warps)
-    // A lone issuing thread is instruction-bound: next to the UTCHMMA stream every scalar instruction of the
-    // k-block bookkeeping costs ~10 cycles, and the tensor pipe idles whenever the thread is not inside an
-    // MMA issue (ncu: tensor pipe 31-56 % active with one issuer, profiles/r01_ncu_conv_single_issuer.md).
-    // Two warps on different SM sub-partitions therefore issue ALTERNATE chunks.  Chunk g (global count)
-    // lives in accumulator slot g % NBUF and NBUF is even, so each slot is only ever written by one issuer
-    // and the order of additions into every accumulator is fixed: results stay bit-deterministic.
-    const uint32_t me = (warp == 3) ? 1u : 0u;
-#if LM_OPERAND_F16
-    const uint32_t idesc_wide = make_idesc_f16(BM, 2 * BN), idesc_corr = make_idesc_f16(BM, BN);
-#define LM_UMMA_C umma_f16_c
-#define LM_UMMA umma_f16
-#else
-    const uint32_t idesc_wide = make_idesc_tf32(BM, 2 * BN), idesc_corr = make_idesc_tf32(BM, BN);
-#define LM_UMMA_C umma_tf32_c
-#define LM_UMMA umma_tf32
-#endif
-    // shared-memory descriptors as (lo, hi) words: lo = start>>4 | LBO, hi = SBO | version | swizzle.
-    // A: K-major SW128 entered at an arbitrary 128-byte row, 8-row group stride = one patch row.
-    const uint32_t desc_hi_a = (uint32_t)((patch_w * 128) >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t desc_hi_b = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t a_base_lo = __shfl_sync(0xffffffffu, ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16), 0);
-    const uint32_t b_base_lo = __shfl_sync(0xffffffffu, ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | (1u << 16), 0);
-    const uint32_t a_lo_plane = (uint32_t)a_plane_bytes >> 4;
-    const uint32_t tap_row_step = (uint32_t)(patch_w - 2) * 8u;  // 16-byte units from (dy, dx=2) to (dy+1, dx=0)
-    const uint64_t hi_a = (uint64_t)desc_hi_a << 32, hi_b = (uint64_t)desc_hi_b << 32;
-    // walking state over ALL k-blocks of the CTA (both issuers walk the same sequence, each issues its own chunks)
-    uint32_t s = 0, ph = 0, ab = 0, aph = 0;
-    uint32_t b_lo = b_base_lo, a_lo_buf = a_base_lo;
-    uint32_t gc = 0;  // global chunk counter
-    uint32_t tseq = 0;  // tiles processed by this CTA: the epilogue group (BN = 64) of a tile is tseq & 1
-    for (int tile = blockIdx.x; tile < total_tiles && (dual_issue || me == 0u); tile += gridDim.x, ++tseq) {
-      const uint32_t tfull_t = tfull0 + 8 * ((EGROUPS == 2 ? (tseq & 1u) : 0u) * NBUF);
-      int tap = 0, dx = 0;
-      uint32_t alo = a_lo_buf;
-      bool a_seen = false;  // this issuer has already waited for the current activation buffer
-      int kb = 0;
-      for (int c = 0; c < num_chunks; ++c, ++gc) {
-        const int kend = min(num_kb, kb + chunk_kb);
-        const bool mine = dual_issue ? ((gc & 1u) == me) : (me == 0u);
-        const uint32_t buf = gc % NBUF, bph = (gc / NBUF) & 1;
-        const uint32_t d_tmem = tmem_base + buf * C::ACC_COLS;
-        if (mine) { LM_PROF_T0(); mbar_wait(tempty0 + 8 * buf, bph ^ 1); if (lane == 0) LM_PROF_ADD(2); }
-        bool first = true;                       // first k-step of the chunk: hi*hi restarts from zero
-        const uint32_t corr_acc = c >= NBUF;     // first use of this slot in the tile: corrections restart too
-        for (; kb < kend; ++kb) {
-          const bool last_tap = (tap == taps - 1);
-          if (mine) {
-            if (!a_seen) { LM_PROF_T0(); mbar_wait(afull0 + 8 * ab, aph); if (lane == 0) LM_PROF_ADD(3); a_seen = true; }
-            { LM_PROF_T0(); mbar_wait(full0 + 8 * s, ph); if (lane == 0) LM_PROF_ADD(4); }
-            tc_fence_after();
-            LM_PROF_T0();
-            const bool last_kb = (kb == kend - 1);
-            if (elect_one()) {
-              if (first) {
-                LM_UMMA_C<false>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_corr);                                          // hi*hi := (zero init)
-                LM_UMMA(d_tmem + BN, hi_a | alo, hi_b | (b_lo + (uint32_t)(C::B_PLANE_BYTES >> 4)), idesc_corr, corr_acc);  // hi*lo
-              } else {
-                if (!(LM_EXP & 16)) LM_UMMA_C<true>(d_tmem, hi_a | alo, hi_b | b_lo, idesc_wide);                       // [hi*hi | hi*lo] +=
-              }
-              if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + a_lo_plane), hi_b | b_lo, idesc_corr);      // lo*hi
-#pragma unroll
-              for (int k = 1; k < ROW_BYTES / 32; ++k) {
-                const uint32_t ko = (uint32_t)(k * 2);  // one MMA k-step = 32 B along K (16 fp16 / 8 tf32), >>4
-                if (!(LM_EXP & 16)) LM_UMMA_C<true>(d_tmem, hi_a | (alo + ko), hi_b | (b_lo + ko), idesc_wide);
-                if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + a_lo_plane + ko), hi_b | (b_lo + ko), idesc_corr);
-              }
-              umma_commit(empty0 + 8 * s);                  // weight stage consumed (only this issuer read it)
-              if (last_tap) umma_commit(aempty0 + 8 * ab);  // this issuer is done with the activation buffer
-              if (last_kb) umma_commit(tfull_t + 8 * buf);  // chunk complete -> the tile's epilogue group may drain it
-            }
-            __syncwarp();
-            if (lane == 0) LM_PROF_ADD(5);
-            first = false;
-          } else if (last_tap && dual_issue) {
-            // not my k-block, but both issuers release every activation buffer (barrier count 2); the commit
-            // arrives once MY earlier MMAs (which may have read the buffer) have retired
-            if (elect_one()) umma_commit(aempty0 + 8 * ab);
-            __syncwarp();
-          }
-          if (++s == STAGES) { s = 0; ph ^= 1; b_lo = b_base_lo; } else b_lo += (uint32_t)(C::STAGE_BYTES >> 4);
-          if (last_tap) {
-            tap = 0; dx = 0; a_seen = false;
-            if (++ab == NUM_A_BUFS) { ab = 0; aph ^= 1; a_lo_buf = a_base_lo; } else a_lo_buf += (uint32_t)(A_BUF_BYTES >> 4);
-            alo = a_lo_buf;
-          } else {
-            ++tap;
-            if (++dx == 3) { dx = 0; alo += tap_row_step; } else alo += 8u;
-          }
-        }
+    // ------------------------------------------------------------------ MMA issuers (two warps, one lane each)
+    // ncu (profiles/r02_ncu_conv_issuer.md) showed the previous warp-uniform issue loops spending ~60 % of their
+    // time in per-k-block bookkeeping (~150 scalar instructions at ~8 cycles each for a lone warp), with the tensor
+    // pipe idle meanwhile.  The loop therefore runs in ONE lane, the nine taps are unrolled with compile-time
+    // descriptor offsets, and the state per k-block is a ring index, a phase bit and a chunk counter.
+    if (elect_one()) {  // (elect.sync, not lane == 0: the compiler then knows the region is single-lane and
+                        //  feeds the MMA's uniform-register operands without per-lane broadcast loops)
+      const uint32_t me = (warp == 3) ? 1u : 0u;
+      if (dual_issue || me == 0u) {
+        IssueArgs ia;
+        ia.me = me; ia.first_tile = (int)blockIdx.x; ia.total_tiles = total_tiles; ia.tile_step = (int)gridDim.x;
+        ia.num_cb = num_cb; ia.chunk_kb = chunk_kb; ia.tmem_base = tmem_base;
+        ia.smem_a = smem_u32(smem); ia.smem_b = smem_u32(smem_b);
+        ia.full0 = full0; ia.empty0 = empty0; ia.tfull0 = tfull0; ia.tempty0 = tempty0; ia.afull0 = afull0; ia.aempty0 = aempty0;
+        if (dual_issue) { if (taps == 9) mma_issue_loop<BN, 9, true>(ia); else mma_issue_loop<BN, 1, true>(ia); }
+        else            { if (taps == 9) mma_issue_loop<BN, 9, false>(ia); else mma_issue_loop<BN, 1, false>(ia); }
       }
     }
+    __syncwarp();
   } else if (warp >= EPI_WARP0) {
     // ------------------------------------------------------------------ epilogue warps
     const int q = warp & 3;

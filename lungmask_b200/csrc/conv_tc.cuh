@@ -52,6 +52,7 @@ struct ConvParams {
   int mode;           // ConvMode
   int chunk_kb;       // k-blocks (kBK channels x 1 tap) accumulated inside the tensor core before the
                       // partial sum is added, round-to-nearest, into fp32 registers
+  int dual_issue;     // 1: two MMA-issuing threads take alternate chunks (0: one issuer)
   const float* bias;  // [Cout]
   const float* scale; // [Cout]  folded BN:  y = relu(.) * scale + shift
   const float* shift; // [Cout]

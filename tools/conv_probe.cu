@@ -2,7 +2,7 @@
 // procedurally generated data (every element is a hash of its index, so the host can evaluate any
 // output pixel without holding the tensors), then times the 22 tensor-core layers of the U-Net at a
 // given batch. Test infrastructure only.
-//   usage: conv_probe [batch=8] [chunk_kb=4] [timing_only=0]
+//   usage: conv_probe [batch=8] [chunk_kb=4] [timing_only=0] [dual_issue=0]
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -106,6 +106,7 @@ static float h_param(uint32_t seed, int c, int kind, bool ints) {
   return kind == 1 ? 1.0f + 0.3f * g : 0.2f * g;
 }
 
+static int g_dual = 0;
 static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool check, bool ints, int reps) {
   const int Cin = L.C0 + L.C1;
   const float wscale = 1.0f / sqrtf((float)Cin * L.taps) * 1.7f;
@@ -142,7 +143,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
 
   ConvParams p{};
   p.N = N; p.H = L.H; p.W = L.W; p.C0 = L.C0; p.C1 = L.C1; p.Cout = L.Cout; p.taps = L.taps; p.mode = L.mode;
-  p.chunk_kb = chunk_kb; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
+  p.chunk_kb = chunk_kb; p.dual_issue = g_dual; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
   p.head_w = b.hw; p.head_b = b.hb; p.K = L.K; p.labels = b.labels; p.scores = b.scores; p.range_flag = b.range_flag;
   ConvMaps maps;
   int r = make_conv_maps(&maps, b.src0, b.src1, b.w, p, N);
@@ -276,9 +277,10 @@ int main(int argc, char** argv) {
   const int batch = argc > 1 ? atoi(argv[1]) : 8;
   const int chunk = argc > 2 ? atoi(argv[2]) : 4;
   const int timing_only = argc > 3 ? atoi(argv[3]) : 0;
+  g_dual = argc > 4 ? atoi(argv[4]) : 0;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
-  printf("device %s SMs %d; batch %d chunk_kb %d\n", prop.name, sms, batch, chunk);
+  printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d\n", prop.name, sms, batch, chunk, g_dual);
   if (!timing_only) {
     const Layer small[] = {
         {"ints 1tile", 16, 8, kBK, 0, 64, 9, kModeReluBn, 0},
