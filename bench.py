@@ -28,8 +28,8 @@ sys.path.insert(0, ROOT)
 S_VOL, RES = 300, 256
 GFLOP_PER_SLICE_TC = 96.20 - 0.0755  # all convs minus the 1->64 stem (CUDA cores); K=3
 # mean dram__bytes_read.sum + dram__bytes_write.sum per conv_tc_kernel launch from the committed ncu --set full capture
-# (profiles/r01_ncu_summary.md, 4 launches of the 37-slice wave); the kernel is tensor/issue bound, DRAM runs at 5-11 % of peak
-TRAFFIC_BYTES_PER_LAUNCH = 399.4e6
+# (profiles/r01_ncu_summary_v5.md, 4 launches of a 37-slice wave); the kernel is issue / tensor bound, DRAM runs at 5-10 % of peak
+TRAFFIC_BYTES_PER_LAUNCH = 188.7e6
 WORKLOAD = "R231 (3-class) 300-slice 256x256 int16 synthetic CT volume per GPU, batch_size=20 (engine waves of 37 slices)"
 
 

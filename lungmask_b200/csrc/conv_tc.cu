@@ -7,32 +7,34 @@
 // (resunet.py:69-70, mask.py:184-186, fused into the last convolution's epilogue).
 //
 // GEMM view: M = 128 output pixels (a 16-row x 8-column patch of one image), N = BN output channels,
-// K = taps * Cin walked in k-blocks of 32 input channels of one filter tap.
-//   * A operand: ONE 5-D TMA box per 32-channel block - the patch plus its one-pixel halo,
-//     (32 ch, 10 x, 18 y, 2 planes, 1 image) = 180 rows of 128 B per plane - serves all nine taps: the tap
+// K = taps * Cin walked in k-blocks of BK input channels of one filter tap, BK = one 128-byte row of the operand
+// format (conv_tc.cuh: 64 fp16 or 32 tf32 channels).
+//   * A operand: ONE 5-D TMA box per BK-channel block - the patch plus its one-pixel halo,
+//     (BK ch, 10 x, 18 y, 2 planes, 1 image) = 180 rows of 128 B per plane - serves all nine taps: the tap
 //     (dy,dx) view is the same shared-memory tile entered at row (dy+1)*10 + (dx+1) with an 8-row-group
 //     stride of 10 rows.  UMMA shared-memory descriptors allow that: the 128B swizzle is a function of the
 //     absolute shared-memory address, so a start address at any 128-byte row and a stride-byte-offset of
 //     1280 B address the rows TMA wrote (checked on B200: profiles/r01_umma_rowoffset_probe.log).  This
 //     cuts the L2->SM traffic of the activations 6.4x versus one box per tap.  TMA zero-fills outside the
 //     image, which IS the convolution's zero padding.
-//   * B operand: one 4-D TMA box (32 cin, BN cout, 1 tap, 2 planes) per k-block.
+//   * B operand: one 4-D TMA box (BK cin, BN cout, 1 tap, 2 planes) per k-block.
 //   * both land 128B-swizzled, K-major, i.e. in the canonical tcgen05 shared-memory layout.
-//   * fp32-class accuracy from tf32 tensor cores: operands are pre-split into tf32 hi + tf32 lo planes
-//     and each k-step computes hi*hi, hi*lo and lo*hi (3xTF32) with TWO instructions: the B tile's hi and
-//     lo planes are adjacent in shared memory, so  A_hi x [B_hi;B_lo]  is one N = 2*BN MMA whose left half
-//     of the accumulator is hi*hi and whose right half is hi*lo; A_lo x B_hi (N = BN) then adds lo*hi into
-//     that right half. The tensor-core accumulator rounds toward zero (measured on B200: -6e-5 relative
-//     drift over K = 8192, profiles/r01_umma_probe.log), so the dominant hi*hi sum is kept apart from the
-//     2^-11-times-smaller corrections and only `chunk_kb` k-blocks (4 MMA k-steps each) of hi*hi are
-//     accumulated in TMEM before the epilogue warps add that partial tile into fp32 registers with
-//     round-to-nearest, while the tensor core already works on the next chunk (NBUF TMEM accumulators of
-//     2*BN columns in a ring). The correction halves are NOT drained per chunk: each ring slot keeps
-//     accumulating its corrections for the whole tile (their drift is 2^-11 times smaller still) and is read
-//     once, with the slot's last chunk - so the per-chunk drain is BN columns, half of the accumulator.
-//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warps 1 and 3 MMA issuers
-//     (alternate chunks), warp 2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter = warp % 4, two warps share a quarter and
-//     split the columns).
+//   * fp32-class accuracy from 11-bit tensor-core operands: every fp32 value is pre-split into a hi and a lo plane
+//     (fp16 hi + fp16 lo * 2^-11 by default, tf32 hi + tf32 lo with LM_OPERAND_F16=0) and each k-step computes
+//     hi*hi, hi*lo and lo*hi - three exact products - with TWO instructions: the B tile's hi and lo planes are
+//     adjacent in shared memory, so  A_hi x [B_hi;B_lo]  is one N = 2*BN MMA whose left half of the accumulator is
+//     hi*hi and whose right half is hi*lo; A_lo x B_hi (N = BN) then adds lo*hi into that right half.  The
+//     tensor-core accumulator rounds toward zero (measured on B200: -6e-5 relative drift over K = 8192,
+//     profiles/r01_umma_probe.log), so the dominant hi*hi sum is kept apart from the 2^-11-times-smaller
+//     corrections and only `chunk_kb` k-blocks (4 MMA k-steps each) of hi*hi are accumulated in TMEM before the
+//     epilogue warps add that partial tile into fp32 registers with round-to-nearest, while the tensor core
+//     already works on the next chunk (NBUF TMEM accumulators of 2*BN columns in a ring).  The correction halves
+//     are NOT drained per chunk: each ring slot keeps accumulating its corrections for the whole tile (their
+//     drift is 2^-11 times smaller still) and is read once, with the slot's last chunk - so the per-chunk drain
+//     is BN columns, half of the accumulator.
+//   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 (and optionally 3) MMA issuer
+//     - one elected lane running mma_issue_loop -, warp 2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter
+//     = warp % 4, two warps share a quarter and split the columns or, for BN = 64, take alternate tiles).
 #include <stdio.h>
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
@@ -330,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1 || warp == 3) {
     // ------------------------------------------------------------------ MMA issuers (two warps, one lane each)
-    // ncu (profiles/r02_ncu_conv_issuer.md) showed the previous warp-uniform issue loops spending ~60 % of their
+    // ncu (profiles/r01_ncu_conv_issuer.md) showed the previous warp-uniform issue loops spending ~60 % of their
     // time in per-k-block bookkeeping (~150 scalar instructions at ~8 cycles each for a lone warp), with the tensor
     // pipe idle meanwhile.  The loop therefore runs in ONE lane, the nine taps are unrolled with compile-time
     // descriptor offsets, and the state per k-block is a ring index, a phase bit and a chunk counter.
