@@ -10,6 +10,12 @@
  * all host buffers; the engine owns all device memory.  One engine drives one CUDA device; calls on
  * one engine must be serialised by the caller.  "dev" variants take device pointers on the engine's
  * device and run on the engine's stream without host copies.
+ *
+ * Numerics: the convolutions carry every fp32 value as an fp16 pair (hi + lo * 2^-11, 22 significant bits) on the
+ * tensor cores and accumulate in fp32; results match the reference's fp32 forward within 1e-4 on the log-softmax
+ * scores.  fp16 saturates at 65504: if a weight (lm_load_weights) or an activation (any call that runs the network)
+ * leaves that range the call fails with LM_ERR_RANGE and the output must be discarded - it never returns a
+ * silently wrong mask.
  */
 #ifndef LUNGMASK_B200_H
 #define LUNGMASK_B200_H
@@ -32,6 +38,7 @@ typedef struct lm_engine lm_engine;
 #define LM_NET_RES 256           /* mask.py:166: utils.preprocess(..., resolution=[256, 256]) */
 #define LM_MAX_SLOTS 4           /* weight slots (e.g. 0 = base model, 1 = fill model) */
 #define LM_FLAG_NO_POSTPROCESS 1 /* LMInferer(volume_postprocessing=False), mask.py:191-194 */
+#define LM_ERR_RANGE (-40)       /* a weight / activation exceeded the fp16 operand range (see "Numerics") */
 
 /* Engine lifetime.  Replaces LMInferer.__init__'s device pick + model.to(device), mask.py:118-139.
  * batch_capacity = slices per forward wave (the reference's batch_size only bounds memory, results
@@ -102,12 +109,13 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * stream; read the sum with lm_last_conv_timing after an lm_apply_volume* call), "chunk_kb" (k-blocks
  * accumulated inside the tensor core between fp32 round-to-nearest adds; sets both layer classes),
  * "chunk_kb_wide" (the same for the layers with >= 128 output channels only; defaults: 1 for the 64-channel
- * layers, 2 for the wide ones). */
+ * layers, 2 for the wide ones), "dual_issue" (0/1: a second MMA-issuing thread per CTA on alternate chunks;
+ * default 0), "post_debug_stage" (parity taps of the post-processing). */
 LM_API int lm_set_option(lm_engine* e, const char* key, int value);
 LM_API int lm_last_conv_timing(const lm_engine* e, float* conv_ms, int64_t* conv_launches);
 
 /* Parity taps: intermediate activations of the LAST forward wave, as fp32 [n][H][W][C] (channels last; the
- * tf32 hi/lo planes are summed).  Activation ids follow the execution order of the network:
+ * hi/lo operand planes are joined).  Activation ids follow the execution order of the network:
  * 0 A0(stem out) 1 S0 2 P0 3 A1 4 S1 5 P1 6 A2 7 S2 8 P2 9 A3 10 S3 11 P3 12 A4 13 B4 (encoder: A = first conv,
  * S = block output / skip, P = pooled) 14 L0 15 U0 16 C0 17 E0 18 L1 19 U1 20 C1 21 E1 22 L2 23 U2 24 C2 25 E2
  * 26 L3 27 U3 28 C3 (decoder: L = 1x1 conv below the upsample, U = upsampled, C = first conv, E = block output). */

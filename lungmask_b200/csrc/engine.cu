@@ -303,7 +303,7 @@ int check_range(lm_engine* e) {
   if (*e->h_range) {
     *e->h_range = 0;
     cudaMemsetAsync(e->d_range, 0, sizeof(int), e->st);
-    return fail(-40, "an activation exceeded the fp16 operand range (|x| > 65504); the result is invalid "
+    return fail(LM_ERR_RANGE, "an activation exceeded the fp16 operand range (|x| > 65504); the result is invalid "
                      "(rebuild with -DLM_OPERAND_F16=0 for the tf32 operand format)");
   }
   return 0;
@@ -438,7 +438,7 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   if (*e->h_range) {
     *e->h_range = 0;
     CU(cudaMemsetAsync(e->d_range, 0, sizeof(int), e->st));
-    return fail(-40, "lm_load_weights: a convolution weight exceeds the fp16 operand range (|w| > 65504)");
+    return fail(LM_ERR_RANGE, "lm_load_weights: a convolution weight exceeds the fp16 operand range (|w| > 65504)");
   }
   for (int i = 0; i < NUM_LAYERS; ++i) {
     const LayerSpec& L = LAYERS[i];
