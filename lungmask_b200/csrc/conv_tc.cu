@@ -666,7 +666,13 @@ int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const voi
   cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)p.Cout, (cuuint64_t)p.taps, 2};
   cuuint64_t strides[3] = {(cuuint64_t)Cin * E, (cuuint64_t)p.Cout * Cin * E, (cuuint64_t)p.taps * p.Cout * Cin * E};
   cuuint32_t box[4] = {BK, (cuuint32_t)BN, 1, 2};
-  return encode(&maps->b, kOpType, weights, 4, dims, strides, box);
+  r = encode(&maps->b, kOpType, weights, 4, dims, strides, box);
+  if (r) return r;
+  // weight boxes of the CTA-pair kernel (optional: a failure only disables that kernel)
+  cuuint32_t box_x[4] = {BK, (cuuint32_t)BN, 1, 1}, box_yw[4] = {BK, (cuuint32_t)(BN / 2), 1, 2};
+  maps->pair_ok = (encode(&maps->bx, kOpType, weights, 4, dims, strides, box_x) == 0 &&
+                   encode(&maps->byw, kOpType, weights, 4, dims, strides, box_yw) == 0) ? 1 : 0;
+  return 0;
 }
 
 template <int BN>

@@ -70,6 +70,10 @@ struct ConvParams {
 struct ConvMaps {
   CUtensorMap a0, a1, b;
   CUtensorMap out, pool;  // TMA-store maps of the output tile (mode 0/1/2) and of the pooled tile (mode 1)
+  // weight boxes of the CTA-pair kernel (conv_tc_pair.cu): bx = (BK cin, BN cout, 1 tap, 1 plane),
+  // byw = (BK cin, BN/2 cout, 1 tap, 2 planes); pair_ok = both were encoded
+  CUtensorMap bx, byw;
+  int pair_ok;
 };
 
 // Builds the TMA descriptors. src1 may be nullptr when C1 == 0. Returns 0 on success.
@@ -78,6 +82,9 @@ int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const voi
 
 // Launches the convolution on `stream`. Returns a cudaError_t value (0 = ok).
 int launch_conv_tc(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);
+
+// CTA-pair variant (conv_tc_pair.cu, tcgen05 cta_group::2; experimental, see the file header). Same contract.
+int launch_conv_tc_pair(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);
 
 // BN (output-channel tile) chosen for a given Cout.
 inline int conv_tile_n(int cout) { return cout >= 128 ? 128 : 64; }

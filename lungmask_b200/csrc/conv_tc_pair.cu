@@ -1,0 +1,557 @@
+// CTA-PAIR variant of conv_tc.cu (tcgen05 cta_group::2): two CTAs of a 2-CTA cluster (one TPC) compute two 128-pixel
+// tiles of the SAME output-channel block with ONE MMA instruction stream (M = 256), issued by the pair's leader.
+//
+//   STATUS: written at the end of round 1 without GPU time left - it compiles (sm_100a) but has NOT run yet.
+//   It is reachable only through lm_set_option("cta_pairs", 1) / tools/conv_probe's 5th argument and is not part
+//   of any default path.  Validate with `tools/conv_probe 37 1 0 0 1` (the CHECK lines) before enabling it.
+//
+// Why (profiles/r01_ncu_conv_issuer.md): the single-CTA kernel is bound by the issuing thread (the tensor pipe waits
+// for it about a third of the time) and, next, by shared-memory bandwidth (121 KB per k-block = 945 cycles for
+// BN = 128 against an 832-cycle tensor floor).  A pair halves the MMA instructions per FLOP and the weight bytes each
+// SM reads: every CTA keeps its own activation patch (A: its 128 rows of M) and HALF of the weight rows of every MMA
+// (B: N/2 rows from each CTA's shared memory at the same offset).
+//
+// Differences from conv_tc.cu (everything else - tiles, halo-reuse A operand, hi/lo operand planes, chunked
+// accumulation, epilogues, TMA stores - is identical; the epilogue code is a verbatim copy):
+//   * weight stage of one k-block in each CTA (2*BN rows of 128 B, as before, but different rows):
+//       X  (BN rows)    leader: B_hi[n0 .. n0+BN)            peer: B_lo[n0 .. n0+BN)
+//       Y  (BN/2 rows)  leader: B_hi[n0 .. n0+BN/2)          peer: B_hi[n0+BN/2 .. n0+BN)
+//       W  (BN/2 rows)  leader: B_lo[n0 .. n0+BN/2)          peer: B_lo[n0+BN/2 .. n0+BN)
+//     wide MMA  A_hi x X  (N = 2*BN): columns [0,BN) = hi*hi (leader's rows), [BN,2BN) = hi*lo (peer's rows);
+//     corr MMA  A_lo x Y  (N = BN)  : lo*hi;  a chunk's first k-step uses A_hi x Y (hi*hi :=), A_hi x W (hi*lo), A_lo x Y.
+//     Two TMA boxes per k-block and CTA: X = (64 cin, BN cout, 1 tap, plane = rank), [Y|W] = (64, BN/2 at
+//     n0 + rank*BN/2, 1 tap, 2 planes).
+//   * "full" barriers (weights, activations) live in the LEADER: count 2 = one arrive per CTA's producer, transaction
+//     bytes of both CTAs (the peer's TMA loads complete on the leader's barrier: .cta_group::2 + peer-bit-masked
+//     barrier address); "empty" / "accumulator ready" barriers are per CTA and are signalled by
+//     tcgen05.commit.cta_group::2 ... multicast::cluster to both; "accumulator drained" lives in the leader with
+//     count 2 x epilogue warps (the peer's epilogue warps arrive remotely).
+//   * TMEM is allocated with cta_group::2 by warp 2 of both CTAs; cluster barriers bracket the kernel body.
+//   * one MMA issuer (the leader's warp 1); grid = pairs * 2, cluster dimension 2.
+#include <stdio.h>
+#include "conv_tc.cuh"
+#include "sm100_ptx.cuh"
+
+namespace lm {
+#define LM_PROF_T0()
+#define LM_PROF_ADD(slot)
+#undef LM_EXP
+#define LM_EXP 0
+namespace {
+
+constexpr int BM = 128, BK = kBK, TILE_H = 16, TILE_W = 8;  // BK channels = one 128-byte row (64 fp16 / 32 tf32)
+constexpr int ROW_BYTES = 128;
+constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
+constexpr int A_PLANE_BYTES_3x3 = HALO_W * HALO_H * ROW_BYTES;  // 180 rows x 128 B = 23040 B per plane
+constexpr int A_PLANE_BYTES_1x1 = BM * ROW_BYTES;               // 16 KB per plane
+constexpr int F32_ROW_CH = 32;                                  // channels per staged 128-byte row of an fp32 output
+constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB (both planes), 1024-aligned
+constexpr int NUM_A_BUFS = 2;
+constexpr int OUT_STAGE_BYTES = BM * 128;  // output staging: 8 epilogue warps x 4 KB (32 pixels x 32 channels fp32), x2 halves
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr int NUM_EPI_THREADS = 256;
+constexpr int MAX_CLASSES = 8;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_PLANE_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * B_PLANE_BYTES;      // one weight tile (hi + lo planes) per k-block
+  static constexpr int STAGES = (BN == 64) ? 6 : 3;
+  static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
+  static constexpr int NBUF = 512 / ACC_COLS;      // accumulator ring: 2 slots (BN=128), 4 slots (BN=64)
+  static constexpr int TMEM_COLS = NBUF * ACC_COLS;
+  // Epilogue organisation.  BN = 128: the 8 epilogue warps split every tile's columns in two halves (64 per thread).
+  // BN = 64: a thread can hold a full row (64 columns), so the warps form TWO GROUPS that take alternate tiles:
+  // while one group runs the tile-end epilogue (BN, split, TMA stores - a third of a short 18-k-block tile), the
+  // other already drains the next tile's chunks and the tensor pipe never waits for a free accumulator slot.
+  static constexpr int HALVES = (BN == 64) ? 1 : 2;
+  static constexpr int EGROUPS = (BN == 64) ? 2 : 1;
+  static constexpr int DYN_SMEM = NUM_A_BUFS * A_BUF_BYTES + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;
+};
+
+struct TileCoord {
+  int n, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(int tile, int n_tiles, int tiles_x, int tiles_img, int BN) {
+  TileCoord t;
+  const int mt = tile / n_tiles;
+  t.n0 = (tile - mt * n_tiles) * BN;
+  t.n = mt / tiles_img;
+  const int r = mt - t.n * tiles_img;
+  const int ty = r / tiles_x;
+  t.y0 = ty * TILE_H;
+  t.x0 = (r - ty * tiles_x) * TILE_W;
+  return t;
+}
+
+struct IssueArgs {
+  int first_pair, total_pairs, pair_step, num_cb, chunk_kb;
+  uint32_t tmem_base, smem_a, smem_b;
+  uint32_t full0, empty0, tfull0, tempty0, afull0, aempty0;  // mbarrier arrays (shared-memory addresses, leader CTA)
+};
+
+// The MMA issue loop of the pair's leader (one elected lane): conv_tc.cu's mma_issue_loop<BN, TAPS, false> with
+// cta_group::2 instructions, the X / Y / W weight-stage layout and multicast commits.
+template <int BN, int TAPS>
+__device__ __forceinline__ void mma_issue_loop_pair(const IssueArgs& g) {
+  using C = Cfg<BN>;
+  constexpr uint32_t STAGES = C::STAGES, NBUF = C::NBUF;
+  constexpr int EGROUPS = C::EGROUPS;
+  constexpr int PATCH_W = (TAPS == 9) ? HALO_W : TILE_W;
+  constexpr uint32_t A_PLANE = (uint32_t)((TAPS == 9) ? A_PLANE_BYTES_3x3 : A_PLANE_BYTES_1x1) >> 4;
+  constexpr uint32_t B_Y = (uint32_t)(BN * ROW_BYTES) >> 4;                 // Y: after X's BN rows
+  constexpr uint32_t B_W = (uint32_t)((BN + BN / 2) * ROW_BYTES) >> 4;      // W: after Y's BN/2 rows
+  constexpr uint32_t idesc_wide = make_idesc_f16(2 * BM, 2 * BN), idesc_corr = make_idesc_f16(2 * BM, BN);
+  constexpr uint64_t hi_a = (uint64_t)((uint32_t)((PATCH_W * 128) >> 4) | (1u << 14) | (2u << 29)) << 32;
+  constexpr uint64_t hi_b = (uint64_t)((uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29)) << 32;
+  constexpr uint16_t BOTH = 3;
+  const uint32_t a_base_lo = ((g.smem_a & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t b_base_lo = ((g.smem_b & 0x3FFFFu) >> 4) | (1u << 16);
+  const int num_kb = g.num_cb * TAPS, chunk_kb = g.chunk_kb;
+  if (g.first_pair >= g.total_pairs) return;
+
+  uint32_t s = 0, ph = 0, ab = 0, aph = 0;  // weight ring / activation ring position and phase
+  uint32_t gc = 0;                          // chunks closed so far -> slot gc % NBUF
+  uint32_t tseq = 0;                        // tiles processed: the epilogue group (BN = 64) of a tile is tseq & 1
+  int kc = 0;                               // k-blocks already in the open chunk
+  int kb_left = num_kb;                     // k-blocks of the tile still to issue (including the current one)
+  uint32_t cit = 0;                         // chunks of this tile already closed
+  mbar_wait(g.afull0, 0);
+  mbar_wait(g.tempty0, 1);
+  mbar_wait(g.full0, 0);
+
+  for (int pt = g.first_pair; pt < g.total_pairs; pt += g.pair_step) {
+    const bool last_tile = pt + g.pair_step >= g.total_pairs;
+    for (int cb = 0; cb < g.num_cb; ++cb) {
+      const uint32_t a_cb = a_base_lo + ab * (uint32_t)(A_BUF_BYTES >> 4);
+      const uint32_t ab_cur = ab;
+      const bool last_cb = (cb == g.num_cb - 1);
+#pragma unroll
+      for (int tap = 0; tap < TAPS; ++tap) {
+        const uint32_t tap_off = (TAPS == 9) ? (uint32_t)(((tap / 3) * PATCH_W + (tap % 3)) * 8) : 0u;
+        const uint32_t buf = gc % NBUF;
+        const uint32_t d_tmem = g.tmem_base + buf * (uint32_t)C::ACC_COLS;
+        const uint32_t alo = a_cb + tap_off;
+        const uint32_t blo = b_base_lo + s * (uint32_t)(C::STAGE_BYTES >> 4);
+        const bool first = (kc == 0);
+        const uint32_t s_cur = s;
+        // ---- first part of the burst
+        tc_fence_after();
+        if (first) {
+          umma_f16_pair_c<false>(d_tmem, hi_a | alo, hi_b | (blo + B_Y), idesc_corr);                        // hi*hi :=
+          umma_f16_pair(d_tmem + BN, hi_a | alo, hi_b | (blo + B_W), idesc_corr, cit >= NBUF ? 1u : 0u);     // hi*lo
+        } else {
+          umma_f16_pair_c<true>(d_tmem, hi_a | alo, hi_b | blo, idesc_wide);                                 // [hi*hi | hi*lo] +=
+        }
+        umma_f16_pair_c<true>(d_tmem + BN, hi_a | (alo + A_PLANE), hi_b | (blo + B_Y), idesc_corr);          // lo*hi
+        umma_f16_pair_c<true>(d_tmem, hi_a | (alo + 2u), hi_b | (blo + 2u), idesc_wide);
+        umma_f16_pair_c<true>(d_tmem + BN, hi_a | (alo + A_PLANE + 2u), hi_b | (blo + B_Y + 2u), idesc_corr);
+        // ---- close the bookkeeping of this k-block, advance to the next one and wait for its barriers
+        --kb_left;
+        const bool chunk_end = (++kc == chunk_kb) || (kb_left == 0);
+        const uint32_t tfull_cur = g.tfull0 + 8 * ((EGROUPS == 2 ? (tseq & 1u) : 0u) * NBUF + buf);
+        if (chunk_end) { kc = 0; ++gc; ++cit; }
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+        bool has_next = true;
+        if (tap == TAPS - 1) {
+          if (++ab == (uint32_t)NUM_A_BUFS) { ab = 0; aph ^= 1u; }
+          if (last_cb) {
+            has_next = !last_tile;
+            kb_left = num_kb; cit = 0; ++tseq;
+          }
+          if (has_next) mbar_wait(g.afull0 + 8 * ab, aph);
+        }
+        if (has_next) mbar_wait(g.full0 + 8 * s, ph);
+        // ---- rest of the burst, then the releases (to both CTAs)
+#pragma unroll
+        for (int k = 2; k < ROW_BYTES / 32; ++k) {
+          const uint32_t ko = (uint32_t)(k * 2);
+          umma_f16_pair_c<true>(d_tmem, hi_a | (alo + ko), hi_b | (blo + ko), idesc_wide);
+          umma_f16_pair_c<true>(d_tmem + BN, hi_a | (alo + A_PLANE + ko), hi_b | (blo + B_Y + ko), idesc_corr);
+        }
+        umma_commit_pair(g.empty0 + 8 * s_cur, BOTH);
+        if (chunk_end) umma_commit_pair(tfull_cur, BOTH);
+        if (tap == TAPS - 1) umma_commit_pair(g.aempty0 + 8 * ab_cur, BOTH);
+        if (has_next && kc == 0) mbar_wait(g.tempty0 + 8 * (gc % NBUF), (((gc / NBUF) & 1u) ^ 1u));
+      }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmBX, const __grid_constant__ CUtensorMap tmBYW,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPool,
+                    const ConvParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int NBUF = C::NBUF;
+  constexpr int HALVES = C::HALVES, EGROUPS = C::EGROUPS;
+  constexpr int NC = BN / HALVES;  // accumulator columns held by one epilogue thread (64)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + (EGROUPS + 1) * NBUF + 2 * NUM_A_BUFS];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_head_w[MAX_CLASSES * 64];
+  __shared__ float s_head_b[MAX_CLASSES];
+
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + EGROUPS * NBUF]);
+  const uint32_t afull0 = smem_u32(&bars[2 * STAGES + (EGROUPS + 1) * NBUF]), aempty0 = afull0 + 8 * NUM_A_BUFS;
+  uint8_t* smem_b = smem + NUM_A_BUFS * A_BUF_BYTES;
+  uint8_t* smem_out = smem_b + STAGES * C::STAGE_BYTES;  // 2 x 16 KB, 1024-aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int tiles_x = p.W / TILE_W, tiles_img = tiles_x * (p.H / TILE_H);
+  const int n_tiles = p.Cout / BN;
+  const int total_pairs = p.N * tiles_img * n_tiles / 2;  // pairs of pixel tiles sharing one output-channel block
+  const uint32_t rank = cluster_ctarank();                // 0 = leader (issues the MMAs), 1 = peer
+  const int first_pair = (int)(blockIdx.x >> 1), pair_step = (int)(gridDim.x >> 1);
+  // this CTA's tile of pair q: pixel tile 2*(q / n_tiles) + rank, channel block q % n_tiles
+  auto my_tile = [&](int q) { const int mtp = q / n_tiles; return (2 * mtp + (int)rank) * n_tiles + (q - mtp * n_tiles); };
+  const int taps = p.taps;
+  const int num_cb = (p.C0 + p.C1) / BK;
+  const int num_kb = num_cb * taps;
+  const int a_plane_bytes = taps == 9 ? A_PLANE_BYTES_3x3 : A_PLANE_BYTES_1x1;
+  const int halo = taps == 9 ? 1 : 0;
+  const int chunk_kb = p.chunk_kb;
+  const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
+  constexpr int EPI_WARPS_PER_GROUP = NUM_EPI_THREADS / 32 / EGROUPS;
+  if (warp == 0 && lane == 0) {
+    // "full" and "drained" barriers are used in the leader only and collect arrivals of both CTAs
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 2); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < NUM_A_BUFS; ++s) { mbar_init(afull0 + 8 * s, 2); mbar_init(aempty0 + 8 * s, 1); }
+    for (int b = 0; b < EGROUPS * NBUF; ++b) mbar_init(tfull0 + 8 * b, 1);
+    for (int b = 0; b < NBUF; ++b) mbar_init(tempty0 + 8 * b, 2 * EPI_WARPS_PER_GROUP);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmBX); tma_prefetch_desc(&tmBYW);
+    tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmPool);
+  }
+  if (warp == 2) tmem_alloc_pair(smem_u32(&tmem_base_s), C::TMEM_COLS);
+  if (p.mode == kModeHead) {
+    for (int i = threadIdx.x; i < p.K * 64; i += NUM_THREADS) s_head_w[i] = p.head_w[i];
+    if (threadIdx.x < p.K) s_head_b[threadIdx.x] = p.head_b[threadIdx.x];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    uint32_t s = 0, ph = 0, ab = 0, aph = 0;
+    const uint32_t a_tx = 2u * (uint32_t)a_plane_bytes;
+    for (int pq = first_pair; pq < total_pairs; pq += pair_step) {
+      const TileCoord t = decode_tile(my_tile(pq), n_tiles, tiles_x, tiles_img, BN);
+      int c = 0;
+      for (int cb = 0; cb < num_cb; ++cb, c += BK) {
+        mbar_wait(aempty0 + 8 * ab, aph ^ 1);  // this CTA's buffer is free (multicast commit of the pair's MMAs)
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx_leader(afull0 + 8 * ab, 2u * a_tx);  // both CTAs' patches
+          else           mbar_arrive_leader(afull0 + 8 * ab);
+          const uint32_t dst = smem_u32(smem) + ab * A_BUF_BYTES;
+          if (c < p.C0) tma_load_5d_pair(dst, &tmA0, afull0 + 8 * ab, c, t.x0 - halo, t.y0 - halo, 0, t.n);
+          else          tma_load_5d_pair(dst, &tmA1, afull0 + 8 * ab, c - p.C0, t.x0 - halo, t.y0 - halo, 0, t.n);
+        }
+        __syncwarp();
+        if (++ab == NUM_A_BUFS) { ab = 0; aph ^= 1; }
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx_leader(full0 + 8 * s, 2u * (uint32_t)C::STAGE_BYTES);
+            else           mbar_arrive_leader(full0 + 8 * s);
+            const uint32_t dst = smem_u32(smem_b) + s * C::STAGE_BYTES;
+            tma_load_4d_pair(dst, &tmBX, full0 + 8 * s, c, t.n0, tap, (int)rank);                          // X: hi (leader) / lo (peer)
+            tma_load_4d_pair(dst + BN * ROW_BYTES, &tmBYW, full0 + 8 * s, c, t.n0 + (int)rank * (BN / 2), tap, 0);  // [Y | W]
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only, one elected lane)
+    if (rank == 0 && elect_one()) {
+      IssueArgs ia;
+      ia.first_pair = first_pair; ia.total_pairs = total_pairs; ia.pair_step = pair_step;
+      ia.num_cb = num_cb; ia.chunk_kb = chunk_kb; ia.tmem_base = tmem_base;
+      ia.smem_a = smem_u32(smem); ia.smem_b = smem_u32(smem_b);
+      ia.full0 = full0; ia.empty0 = empty0; ia.tfull0 = tfull0; ia.tempty0 = tempty0; ia.afull0 = afull0; ia.aempty0 = aempty0;
+      if (taps == 9) mma_issue_loop_pair<BN, 9>(ia); else mma_issue_loop_pair<BN, 1>(ia);
+    }
+    __syncwarp();
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int half = (HALVES == 2) ? ((warp - EPI_WARP0) >> 2) : 0;
+    const uint32_t egroup = (EGROUPS == 2) ? (uint32_t)((warp - EPI_WARP0) >> 2) : 0u;
+    const int row = q * 32 + lane, hl = row >> 3, wl = row & 7;  // 16 x 8 patch, 8 pixels per image row
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t tfull_g = tfull0 + 8 * (egroup * NBUF);
+    uint32_t buf = 0;          // ring slot of the next chunk (all tiles, both groups, advance it)
+    uint32_t phase_bits = 0;   // bit b: parity this group's next wait on slot b expects (its own barrier set)
+    uint32_t tseq = 0;
+    for (int pq = first_pair; pq < total_pairs; pq += pair_step, ++tseq) {
+      if (EGROUPS == 2 && (tseq & 1u) != egroup) { buf = (buf + (uint32_t)num_chunks) % NBUF; continue; }  // the other group's tile
+      const TileCoord t = decode_tile(my_tile(pq), n_tiles, tiles_x, tiles_img, BN);
+      float acc[NC];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+      for (int c = 0; c < num_chunks; ++c) {
+        { LM_PROF_T0(); mbar_wait(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
+        phase_bits ^= 1u << buf;
+        tc_fence_after();
+        LM_PROF_T0();
+        const uint32_t col0 = tmem_base + lane_base + buf * C::ACC_COLS + half * NC;
+        const bool last_use = c >= num_chunks - NBUF;  // this slot is not written again in this tile
+        // all TMEM reads of this slot first, then hand the slot back BEFORE the register adds: the
+        // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
+        float v[NC];
+#pragma unroll
+        for (int j = 0; j < NC / 32; ++j) {
+          if (!(LM_EXP & 2) || last_use) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
+        }
+        if (last_use) {
+          float w[NC];
+#pragma unroll
+          for (int j = 0; j < NC / 32; ++j) tmem_ld32(col0 + BN + j * 32, w + j * 32);  // the slot's corrections, whole tile
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty0 + 8 * buf);  // the leader's barrier counts both CTAs' epilogue warps
+#pragma unroll
+          for (int i = 0; i < NC; ++i) acc[i] = (acc[i] + v[i]) + w[i] * kLoUnscale;  // exact power-of-two rescale of hi*lo + lo*hi
+        } else {
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(tempty0 + 8 * buf);  // the leader's barrier counts both CTAs' epilogue warps
+#pragma unroll
+          for (int i = 0; i < NC; ++i) acc[i] += v[i];
+        }
+        if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(7);
+        if (++buf == NBUF) buf = 0;
+      }
+      LM_PROF_T0();
+      const int y = t.y0 + hl, x = t.x0 + wl;
+      const int cbase = t.n0 + half * NC;
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+
+      // The tile leaves through shared memory: every thread drops its pixel's 32-channel groups as 128-byte
+      // rows (128B-swizzled, conflict-free) into its WARP's 4 KB staging buffer (32 pixels = 4 image rows x 8)
+      // and the warp's lane 0 hands the buffer to a TMA store - fully coalesced 128 B bursts instead of 32
+      // scattered 16-byte stores per warp instruction (16-23k cycles per tile, profiles/r01_conv_role_stalls_v2.log)
+      // - with no cross-warp barrier: each epilogue warp streams its own rows out independently.
+      const uint32_t stage = smem_u32(smem_out) + (uint32_t)(warp - EPI_WARP0) * 4096u;
+      const bool issuer = (lane == 0);
+      const int ty0 = t.y0 + 4 * q;  // first image row of this warp's 32 pixels
+      auto stage_row = [&](uint32_t r, const uint32_t* v8x4) {  // 32 words (128 B) -> row r, chunk j at (j ^ (r & 7))
+        if (LM_EXP & 4) {  // keep the values alive, skip the shared-memory traffic
+          uint32_t x = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x ^= v8x4[j];
+          if (x == 0x12345u) p.labels[0] = 1;
+          return;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t addr = stage + r * 128u + (uint32_t)((j ^ (int)(r & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v8x4[4 * j]), "r"(v8x4[4 * j + 1]),
+                       "r"(v8x4[4 * j + 2]), "r"(v8x4[4 * j + 3])
+                       : "memory");
+        }
+      };
+      // one 128-byte row of operand-format channels (BK of them) of plane `plane`, from fp32 values
+      auto pack_row = [&](const float* src, int plane, uint32_t* v) {
+#if LM_OPERAND_F16
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          __half h0, l0, h1, l1;
+          split_f16(src[2 * i], h0, l0);
+          split_f16(src[2 * i + 1], h1, l1);
+          v[i] = plane ? pack_half2(l0, l1) : pack_half2(h0, h1);
+        }
+#else
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float hi, lo;
+          split_tf32(src[i], hi, lo);
+          v[i] = __float_as_uint(plane ? lo : hi);
+        }
+#endif
+      };
+      auto round_begin = [&]() {
+        if (issuer) tma_store_wait_read();  // this warp's previous store has finished reading the buffer
+        __syncwarp();
+      };
+      auto round_end = [&]() {
+        fence_proxy_async();
+        __syncwarp();
+      };
+
+      if (p.mode == kModeLinear) {
+#pragma unroll
+        for (int g = 0; g < NC / F32_ROW_CH; ++g) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(bias4 + g * 8 + i);
+            v[4 * i] = __float_as_uint(acc[g * 32 + 4 * i] + b.x); v[4 * i + 1] = __float_as_uint(acc[g * 32 + 4 * i + 1] + b.y);
+            v[4 * i + 2] = __float_as_uint(acc[g * 32 + 4 * i + 2] + b.z); v[4 * i + 3] = __float_as_uint(acc[g * 32 + 4 * i + 3] + b.w);
+          }
+          round_begin();
+          stage_row((uint32_t)lane, v);
+          round_end();
+          if (issuer && !(LM_EXP & 4)) { tma_store_4d(&tmOut, stage, cbase + g * F32_ROW_CH, t.x0, ty0, t.n); tma_store_commit(); }
+        }
+      } else {
+        const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cbase);
+        const float4* shift4 = reinterpret_cast<const float4*>(p.shift + cbase);
+        // y = relu(acc + bias) * scale + shift   (Conv -> ReLU -> BatchNorm(eval), resunet.py:93-105)
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i) {
+          const float4 b = __ldg(bias4 + i), s = __ldg(scale4 + i), h = __ldg(shift4 + i);
+          acc[4 * i + 0] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 0] + b.x, 0.f), s.x), h.x);
+          acc[4 * i + 1] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 1] + b.y, 0.f), s.y), h.y);
+          acc[4 * i + 2] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 2] + b.z, 0.f), s.z), h.z);
+          acc[4 * i + 3] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 3] + b.w, 0.f), s.w), h.w);
+        }
+        if (p.mode == kModeHead) {
+          // 1x1 head (resunet.py:69): this thread holds all 64 channels of its pixel (BN = 64 rows are not split).
+          float lg[MAX_CLASSES];
+          float mx = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < MAX_CLASSES; ++k) {
+            float sdot = 0.f;
+            if (k < p.K) {
+#pragma unroll
+              for (int i = 0; i < NC; ++i) sdot = fmaf(s_head_w[k * 64 + (half * NC + i) % 64], acc[i], sdot);
+            }
+            lg[k] = (k < p.K) ? sdot + s_head_b[k] : -INFINITY;
+            mx = fmaxf(mx, lg[k]);
+          }
+          float se = 0.f;
+#pragma unroll
+          for (int k = 0; k < MAX_CLASSES; ++k) if (k < p.K) se += expf(lg[k] - mx);
+          const float lse = logf(se);
+          int best = 0;
+          float bestv = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < MAX_CLASSES; ++k) {
+            if (k < p.K) {
+              const float sc = (lg[k] - mx) - lse;  // LogSoftmax(dim=1), resunet.py:70
+              if (sc > bestv) { bestv = sc; best = k; }  // first index wins ties (mask.py:185)
+              if (p.scores) p.scores[(((size_t)t.n * p.K + k) * p.H + y) * p.W + x] = sc;
+            }
+          }
+          p.labels[((size_t)t.n * p.H + y) * p.W + x] = (uint8_t)best;
+        } else {
+#if LM_OPERAND_F16
+          {  // fp16 saturates: report instead of storing inf
+            bool ovf = false;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) ovf |= !(fabsf(acc[i]) <= kOpMax);
+            if (__any_sync(0xffffffffu, ovf) && lane == 0 && p.range_flag) *p.range_flag = 1;
+          }
+#endif
+#pragma unroll
+          for (int g = 0; g < NC / BK; ++g) {
+#pragma unroll
+            for (int plane = 0; plane < 2; ++plane) {
+              uint32_t v[32];
+              pack_row(acc + g * BK, plane, v);
+              round_begin();
+              stage_row((uint32_t)lane, v);
+              round_end();
+              if (issuer && !(LM_EXP & 4)) { tma_store_5d(&tmOut, stage, cbase + g * BK, t.x0, ty0, plane, t.n); tma_store_commit(); }
+            }
+          }
+          if (p.mode == kModeReluBnPool) {
+            // 2x2 average (resunet.py:64): partners are lanes ^1 (x) and ^8 (y) of the same warp; the lane with
+            // even x and y stages the pooled pixel: 8 per warp (2 pooled rows x 4) = rows 0..7 of the warp's buffer.
+            const bool writer = (lane & 9) == 0;
+            const uint32_t prow = (uint32_t)((lane >> 4) * (TILE_W / 2) + ((lane & 7) >> 1));
+#pragma unroll
+            for (int g = 0; g < NC / BK; ++g) {
+              float pv[BK];
+#pragma unroll
+              for (int i = 0; i < BK; ++i) {
+                float s = acc[g * BK + i] + __shfl_xor_sync(0xffffffffu, acc[g * BK + i], 1);
+                s = s + __shfl_xor_sync(0xffffffffu, s, 8);
+                pv[i] = s * 0.25f;
+              }
+#pragma unroll
+              for (int plane = 0; plane < 2; ++plane) {
+                uint32_t v[32];
+                pack_row(pv, plane, v);
+                round_begin();
+                if (writer) stage_row(prow, v);
+                round_end();
+                if (issuer && !(LM_EXP & 4)) { tma_store_5d(&tmPool, stage, cbase + g * BK, t.x0 >> 1, ty0 >> 1, plane, t.n); tma_store_commit(); }
+              }
+            }
+          }
+        }
+      }
+      if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(8);
+    }
+    if (lane == 0) tma_store_wait_all();  // every epilogue warp's issuer: global writes complete before exit
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+template <int BN>
+static int launch_pair_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg<BN>::DYN_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int total_pairs = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN) / 2;
+  const int sm_pairs = num_sms / 2;
+  const int pairs = total_pairs < sm_pairs ? total_pairs : sm_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg<BN>::DYN_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BN>, maps.a0, maps.a1, maps.bx, maps.byw, maps.out, maps.pool, p);
+  return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+
+// Same contract as launch_conv_tc (conv_tc.cuh); `maps` must come from make_conv_maps (which also encodes the pair's
+// weight boxes bx / byw).  Requires an even number of pixel tiles (always true: every level has >= 2 tiles per image).
+int launch_conv_tc_pair(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
+#if !LM_OPERAND_F16
+  return -7;  // the pair kernel is written for the fp16 operand format only
+#else
+  if (p.mode == kModeHead && (p.Cout != 64 || p.K > MAX_CLASSES)) return -4;
+  if (p.chunk_kb < 1) return -5;
+  if (!maps.pair_ok) return -6;
+  if ((p.N * (p.H / TILE_H) * (p.W / TILE_W)) % 2) return -8;
+  return conv_tile_n(p.Cout) == 128 ? launch_pair_impl<128>(maps, p, num_sms, stream)
+                                    : launch_pair_impl<64>(maps, p, num_sms, stream);
+#endif
+}
+
+}  // namespace lm

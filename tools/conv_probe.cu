@@ -2,7 +2,7 @@
 // procedurally generated data (every element is a hash of its index, so the host can evaluate any
 // output pixel without holding the tensors), then times the 22 tensor-core layers of the U-Net at a
 // given batch. Test infrastructure only.
-//   usage: conv_probe [batch=8] [chunk_kb=4] [timing_only=0] [dual_issue=0]
+//   usage: conv_probe [batch=8] [chunk_kb=4] [timing_only=0] [dual_issue=0] [cta_pairs=0]
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -106,7 +106,7 @@ static float h_param(uint32_t seed, int c, int kind, bool ints) {
   return kind == 1 ? 1.0f + 0.3f * g : 0.2f * g;
 }
 
-static int g_dual = 0;
+static int g_dual = 0, g_pair = 0;
 static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool check, bool ints, int reps) {
   const int Cin = L.C0 + L.C1;
   const float wscale = 1.0f / sqrtf((float)Cin * L.taps) * 1.7f;
@@ -149,7 +149,8 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   int r = make_conv_maps(&maps, b.src0, b.src1, b.w, p, N);
   if (r) { printf("make_conv_maps failed %d\n", r); exit(2); }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  r = launch_conv_tc(maps, p, num_sms, 0);
+  auto launch = [&]() { return g_pair ? launch_conv_tc_pair(maps, p, num_sms, 0) : launch_conv_tc(maps, p, num_sms, 0); };
+  r = launch();
   if (r) { printf("launch failed %d\n", r); exit(2); }
   CK(cudaDeviceSynchronize());
   float ms = 0;
@@ -158,7 +159,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
 #endif
   if (reps > 0) {
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; ++i) launch_conv_tc(maps, p, num_sms, 0);
+    for (int i = 0; i < reps; ++i) launch();
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -278,9 +279,10 @@ int main(int argc, char** argv) {
   const int chunk = argc > 2 ? atoi(argv[2]) : 4;
   const int timing_only = argc > 3 ? atoi(argv[3]) : 0;
   g_dual = argc > 4 ? atoi(argv[4]) : 0;
+  g_pair = argc > 5 ? atoi(argv[5]) : 0;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
-  printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d\n", prop.name, sms, batch, chunk, g_dual);
+  printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d cta_pairs %d\n", prop.name, sms, batch, chunk, g_dual, g_pair);
   if (!timing_only) {
     const Layer small[] = {
         {"ints 1tile", 16, 8, kBK, 0, 64, 9, kModeReluBn, 0},
