@@ -14,6 +14,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
 
+if os.environ.get("LM_OPERAND_F16") == "0":   # the range-free tf32-pair operand format (conv_tc.cuh); default is fp16 pairs
+    NVCC_FLAGS.append("-DLM_OPERAND_F16=0")
+
+
 def _nvcc():
     for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
