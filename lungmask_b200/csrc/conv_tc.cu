@@ -677,12 +677,15 @@ int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const voi
 
 template <int BN>
 static int launch_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static unsigned long long attr_set_mask = 0ull;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
+  if (!((attr_set_mask >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BN>::DYN_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set_mask |= 1ull << dev;
   }
   const int total = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN);
   const int grid = total < num_sms ? total : num_sms;

@@ -515,12 +515,15 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
 template <int BN>
 static int launch_pair_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static unsigned long long attr_set_mask = 0ull;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
+  if (!((attr_set_mask >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BN>::DYN_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set_mask |= 1ull << dev;
   }
   const int total_pairs = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN) / 2;
   const int sm_pairs = num_sms / 2;

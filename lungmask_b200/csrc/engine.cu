@@ -401,8 +401,12 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   s.K = K;
   const float* q = blob;
   std::vector<float> scale, shift;
-  float* d_tmp = nullptr;
-  CU(cudaMalloc(&d_tmp, (size_t)1024 * 1024 * 9 * sizeof(float)));
+  struct Tmp {  // staging buffer for one layer's OIHW weights (largest: 1024 x 1024 x 9), freed on every exit path
+    float* p = nullptr;
+    ~Tmp() { if (p) cudaFree(p); }
+  } tmp;
+  CU(cudaMalloc(&tmp.p, (size_t)1024 * 1024 * 9 * sizeof(float)));
+  float* const d_tmp = tmp.p;
   // stem
   RC(upload(&s.stem_w, q, 64 * 9, e->st)); q += 64 * 9;
   RC(upload(&s.stem_bias, q, 64, e->st)); q += 64;
@@ -433,7 +437,6 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   s.head_w = s.head_b = nullptr;
   RC(upload(&s.head_w, q, (size_t)K * 64, e->st)); q += (size_t)K * 64;
   RC(upload(&s.head_b, q, K, e->st)); q += K;
-  cudaFree(d_tmp);
   if ((size_t)(q - blob) != n_floats) return fail(-1, "lm_load_weights: internal blob walk mismatch");
   CU(cudaMemcpyAsync(e->h_range, e->d_range, sizeof(int), cudaMemcpyDeviceToHost, e->st));
   CU(cudaStreamSynchronize(e->st));
