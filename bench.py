@@ -236,7 +236,7 @@ def run_engine(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f16x3 (fp32-class: every fp32 value is an fp16 hi + scaled fp16 lo pair, 3 exact products per MAC, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "volumes_per_step_per_gpu": 1, "slices_per_step": world * S_VOL,
-                       "l2": "inputs larger than L2: 39 MB volume, ~11.5 GB of activations per 37-slice wave",
+                       "l2": "inputs larger than L2: 39 MB volume, ~6 GB of activations per 37-slice wave",
                        "weights": "seeded synthetic state_dict, 60 Adam steps on phantoms (released .pth needs network)",
                        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
                        "mma_issuers_per_cta": 2 if os.environ.get("LM_DUAL_ISSUE", "0") not in ("", "0") else 1,

@@ -120,7 +120,7 @@ class LMInferer:
         LOCAL_RANK or 0) and `wave_slices`.  The reference's `batch_size` only bounds memory (slices are
         independent, mask.py:172-187; the engine is batch-invariant, tests/test_gpu_forward.py); the engine
         runs the forward in waves of `wave_slices` slices, default 37 when batch_size >= 20 because
-        37 x 16 tiles = 4 x 148 SMs fills every level of the U-Net with whole waves of CTAs (11.5 GB of
+        37 x 16 tiles = 4 x 148 SMs fills every level of the U-Net with whole waves of CTAs (6 GB of
         activations), else batch_size."""
         assert modelname in MODEL_URLS, "Modelname not found. Please choose from: {}".format(MODEL_URLS.keys())
         if fillmodel is not None:
