@@ -156,6 +156,7 @@ struct lm_engine {
   int64_t launches = 0;
   int dual_issue = 0;     // 1: two MMA-issuing threads per CTA on alternate chunks (conv_tc.cu)
   int cta_pairs = 0;      // 1: the experimental cta_group::2 kernel (conv_tc_pair.cu; not validated on hardware yet)
+  int stem_v2 = 0;        // 1: stem_kernel_v2 (forward_misc.cu; not validated on hardware yet)
   int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
   int chunk_kb_wide = 2;  // ... for the layers with Cout >= 128 (ring of 2 slots: chunk 1 leaves the tensor pipe waiting
                           // for the drain; chunk 2 costs < 1e-5 of score accuracy there, tools/debug_gpu.py)
@@ -202,7 +203,8 @@ int upload(float** dst, const float* src, size_t n, cudaStream_t st) {
 
 int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_t* d_labels, float* d_scores,
                   bool time_convs) {
-  RC(launch_stem(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R, e->d_range, e->num_sms, e->st));
+  RC((e->stem_v2 ? launch_stem_v2 : launch_stem)(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
+                                                 e->d_range, e->num_sms, e->st));
   e->launches++;
   int up = 0;
   for (int i = 0; i < NUM_LAYERS; ++i) {
@@ -351,6 +353,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = e->chunk_kb_wide = v; }
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
+  if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
   CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&e->ev[i]));
@@ -658,6 +661,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = e->chunk_kb_wide = value; return 0; }
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
+  if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
   if (!strcmp(key, "chunk_kb_wide")) { if (value < 1) return fail(-1, "chunk_kb_wide must be >= 1"); e->chunk_kb_wide = value; return 0; }
   return fail(-1, "lm_set_option: unknown key %s", key);
 }

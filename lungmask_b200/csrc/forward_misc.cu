@@ -92,6 +92,80 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
   if (ovf && range_flag) *range_flag = 1;
 }
 
+// stem_kernel_v2 (opt-in, lm_set_option("stem_v2"); written without GPU time left - validate with
+// LM_TEST_EXPERIMENTAL=1 pytest -m gpu before making it the default).  Same arithmetic in the same order as stem_kernel,
+// different work assignment: ncu shows stem_kernel bound by shared-memory loads (72 weight + 9 LUT loads per thread and
+// pixel, 15 % of the HBM write rate).  Here a thread owns ONE group of CPT output channels for the whole kernel, keeps
+// that group's 9 x CPT weights and 3 x CPT epilogue constants in registers, and walks quads of 4 x-adjacent pixels with
+// an 18-sample (3 x 6) input window: 4.5 LUT loads per pixel and no weight loads.
+template <int QW>
+__global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict__ in, op_t* __restrict__ out,
+                                                      const float* __restrict__ w,      // [64][9]
+                                                      const float* __restrict__ bias,   // [64]
+                                                      const float* __restrict__ scale,  // [64]
+                                                      const float* __restrict__ shift,  // [64]
+                                                      int N, int H, int W, int* __restrict__ range_flag) {
+  __shared__ float lut[1625];
+  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = (float)((double)i / 1624.0);
+  constexpr int TPP = 64 / CPT;  // threads per pixel quad
+  const int cq = (int)(threadIdx.x % TPP);
+  float wr[CPT][9], br[CPT], sr[CPT], hr[CPT];
+#pragma unroll
+  for (int e = 0; e < CPT; ++e) {
+    const int c = cq * CPT + e;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) wr[e][tap] = __ldg(w + c * 9 + tap);
+    br[e] = __ldg(bias + c); sr[e] = __ldg(scale + c); hr[e] = __ldg(shift + c);
+  }
+  __syncthreads();
+  const size_t plane = (size_t)H * W;
+  const int quads_per_row = W / QW;
+  const size_t total_quads = (size_t)N * H * quads_per_row;
+  const size_t quad0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) / TPP;
+  const size_t quad_step = ((size_t)gridDim.x * blockDim.x) / TPP;
+  bool ovf = false;
+  for (size_t qd = quad0; qd < total_quads; qd += quad_step) {
+    const int qx = (int)(qd % quads_per_row);
+    const size_t rowid = qd / quads_per_row;
+    const int y = (int)(rowid % H);
+    const int n = (int)(rowid / H);
+    const int x0 = qx * QW;
+    const int16_t* img = in + (size_t)n * plane;
+    float win[3][QW + 2];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+#pragma unroll
+      for (int dx = 0; dx < QW + 2; ++dx) {
+        const int xx = x0 + dx - 1;
+        float val = 0.f;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          int hu = img[(size_t)yy * W + xx];
+          hu = hu > 600 ? 600 : hu;  // mask.py:167
+          const int idx = hu + 1024;
+          val = idx >= 0 ? lut[idx] : (float)((double)idx / 1624.0);  // mask.py:168
+        }
+        win[dy][dx] = val;
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < QW; ++px) {
+      float yv[CPT];
+#pragma unroll
+      for (int e = 0; e < CPT; ++e) {
+        float s = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) s = fmaf(wr[e][tap], win[tap / 3][px + tap % 3], s);
+        yv[e] = __fadd_rn(__fmul_rn(fmaxf(s + br[e], 0.f), sr[e]), hr[e]);
+      }
+      const size_t r = (size_t)y * W + x0 + px;
+      op_t* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * CPT;
+      split_store(yv, o, o + plane * 64, ovf);
+    }
+  }
+  if (ovf && range_flag) *range_flag = 1;
+}
+
 // in: [N][h][w][C] fp32 -> out: [N][2][2h][2w][C] split planes. PyTorch semantics (align_corners=False):
 // src = max(0.5*(dst+0.5)-0.5, 0), i0 = (int)src, i1 = i0 + (i0 < size-1), l1 = src - i0, l0 = 1 - l1.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, op_t* __restrict__ out,
@@ -159,6 +233,19 @@ int launch_stem(const int16_t* in, void* out, const float* w, const float* bias,
                 const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream) {
   const size_t total = (size_t)N * H * W * (64 / CPT);
   stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag);
+  return (int)cudaGetLastError();
+}
+
+int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
+                   const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream) {
+  constexpr int QW = 4;
+  if (W % QW) return launch_stem(in, out, w, bias, scale, shift, N, H, W, range_flag, num_sms, stream);
+  const size_t threads = (size_t)N * H * (W / QW) * (64 / CPT);
+  size_t blocks = (threads + 127) / 128;
+  const size_t cap = (size_t)num_sms * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  stem_kernel_v2<QW><<<(int)blocks, 128, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag);
   return (int)cudaGetLastError();
 }
 

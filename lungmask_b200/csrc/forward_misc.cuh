@@ -9,6 +9,9 @@ namespace lm {
 // (range_flag: device int set to 1 when a value leaves the operand format's range; may be nullptr)
 int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
                 const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream);
+// same result from a different work assignment (weights in registers, 4-pixel quads); opt-in, see forward_misc.cu
+int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
+                   const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream);
 // fp32 [N][h][w][C] -> split planes [N][2][2h][2w][C]
 int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream);
 // OIHW fp32 -> [2][taps][Cout][Cin] hi/lo operand planes
