@@ -112,6 +112,7 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * layers, 2 for the wide ones), "dual_issue" (0/1: a second MMA-issuing thread per CTA on alternate chunks;
  * default 0), "cta_pairs" (0/1: the experimental cta_group::2 convolution kernel; default 0),
  * "stem_v2" (0/1: the experimental register-resident stem kernel; default 0),
+ * "ccl_reduced" (0/1: reduced neighbour set in the 26-connected labelling; default 0),
  * "post_debug_stage" (parity taps of the post-processing). */
 LM_API int lm_set_option(lm_engine* e, const char* key, int value);
 LM_API int lm_last_conv_timing(const lm_engine* e, float* conv_ms, int64_t* conv_launches);

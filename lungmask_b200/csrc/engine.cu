@@ -354,6 +354,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
   if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
+  if (const char* c = getenv("LM_CCL_REDUCED")) e->post.ccl_reduced = atoi(c) != 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
   CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&e->ev[i]));
@@ -662,6 +663,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
   if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
+  if (!strcmp(key, "ccl_reduced")) { e->post.ccl_reduced = value != 0; return 0; }
   if (!strcmp(key, "chunk_kb_wide")) { if (value < 1) return fail(-1, "chunk_kb_wide must be >= 1"); e->chunk_kb_wide = value; return 0; }
   return fail(-1, "lm_set_option: unknown key %s", key);
 }

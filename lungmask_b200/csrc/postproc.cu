@@ -71,8 +71,13 @@ __global__ void ccl_init_kernel(const uint8_t* __restrict__ vals, uint32_t* __re
 }
 
 // CONN: 26 (3-D full), 6 (3-D faces), 4 (2-D faces within a slice). Only neighbours inside the box count.
+// reduced != 0 (CONN == 26 only; opt-in, lm_set_option("ccl_reduced")): when the left neighbour carries the same label
+// the voxel is united with it and with its four backward neighbours at dx = +1 only - the other eight backward
+// neighbours are backward neighbours of the left voxel, which unites with them itself.  Same partition, same
+// minimum-index roots (tests/test_ccl_neighbour_rule.py enumerates this on the CPU); 5 instead of 13 probes inside
+// homogeneous regions.
 template <int CONN>
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, Box b) {
+__global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, Box b, int reduced) {
   const size_t n = box_volume(b);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
@@ -81,6 +86,7 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __r
     if (!v) continue;
     const size_t HW = (size_t)d.H * d.W;
     if (CONN == 26) {
+      const bool left = reduced && x > b.x0 && vals[i - 1] == v;
 #pragma unroll
       for (int dz = -1; dz <= 0; ++dz)
 #pragma unroll
@@ -88,6 +94,7 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __r
 #pragma unroll
           for (int dx = -1; dx <= 1; ++dx) {
             if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;  // backward half only
+            if (left && dx != 1 && !(dz == 0 && dy == 0 && dx == -1)) continue;  // covered by the left voxel
             const int zz = z + dz, yy = y + dy, xx = x + dx;
             if (zz < b.z0 || yy < b.y0 || yy >= b.y1 || xx < b.x0 || xx >= b.x1) continue;
             const uint32_t j = (uint32_t)((size_t)zz * HW + (size_t)yy * d.W + xx);
@@ -490,11 +497,11 @@ inline int grid_for(size_t n, int block, int num_sms) {
   } while (0)
 
 template <int CONN>
-int run_ccl(const uint8_t* vals, uint32_t* parent, Dim d, Box b, int num_sms, cudaStream_t st, int64_t* launches) {
+int run_ccl(const uint8_t* vals, uint32_t* parent, Dim d, Box b, int num_sms, cudaStream_t st, int64_t* launches, int reduced = 0) {
   const size_t n = (size_t)(b.z1 - b.z0) * (b.y1 - b.y0) * (b.x1 - b.x0);
   const int g = grid_for(n, 256, num_sms);
   ccl_init_kernel<<<g, 256, 0, st>>>(vals, parent, d, b);
-  ccl_merge_kernel<CONN><<<g, 256, 0, st>>>(vals, parent, d, b);
+  ccl_merge_kernel<CONN><<<g, 256, 0, st>>>(vals, parent, d, b, reduced);
   ccl_flatten_kernel<<<g, 256, 0, st>>>(parent, d, b);
   *launches += 3;
   return (int)cudaGetLastError();
@@ -560,7 +567,7 @@ int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, i
   uint32_t* d_small = reinterpret_cast<uint32_t*>(ws.small);  // [0] R, [8..264) present flags, [512..1024) record etc.
 
   // Q1: components + canonical ids
-  rc = run_ccl<26>(d_labels, ws.parent, d, full, num_sms, st, launches);
+  rc = run_ccl<26>(d_labels, ws.parent, d, full, num_sms, st, launches, ws.ccl_reduced);
   if (rc) return rc;
   const int nb = (int)((n + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS));
   roots_count_kernel<<<nb, SCAN_BLOCK, 0, st>>>(ws.parent, n, ws.block_counts);
@@ -646,7 +653,7 @@ int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, i
   }
   // Q6
   LM_CUDA(cudaMemsetAsync(d_out, 0, n, st));
-  rc = run_ccl<26>(ws.mapped, ws.parent, d, full, num_sms, st, launches);
+  rc = run_ccl<26>(ws.mapped, ws.parent, d, full, num_sms, st, launches, ws.ccl_reduced);
   if (rc) return rc;
   LM_CUDA(cudaMemsetAsync(ws.area2, 0, n * 4, st));
   unsigned long long* d_best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.small) + 8192);
@@ -720,7 +727,7 @@ int keep_largest_component_device(PostScratch& ws, const uint8_t* d_mask, int S,
   const int g = grid_for(n, 256, num_sms);
   int64_t launches = 0;
   binarize_kernel<<<g, 256, 0, st>>>(d_mask, ws.tmp, n);
-  rc = run_ccl<26>(ws.tmp, ws.parent, d, full, num_sms, st, &launches);
+  rc = run_ccl<26>(ws.tmp, ws.parent, d, full, num_sms, st, &launches, ws.ccl_reduced);
   if (rc) return rc;
   LM_CUDA(cudaMemsetAsync(ws.area2, 0, n * 4, st));
   unsigned long long* d_best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.small) + 8192);

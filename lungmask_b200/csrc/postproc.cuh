@@ -9,6 +9,7 @@ namespace lm {
 // Scratch buffers for postprocess_device, grown on demand and reused across calls.
 struct PostScratch {
   size_t cap_vox = 0, cap_regions = 0;
+  int ccl_reduced = 0;  // 1: reduced neighbour set in the 26-connected union-find (postproc.cu; opt-in until run on hardware)
   int debug_stage = 0;  // parity taps: 1 = return the Q5 label map, 2 = region ids & 255, 3 = merged ids & 255
   uint32_t *parent = nullptr, *parent2 = nullptr, *rid = nullptr, *area2 = nullptr;
   uint8_t *mapped = nullptr, *tmp = nullptr, *outside = nullptr;
