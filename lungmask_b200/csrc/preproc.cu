@@ -316,11 +316,13 @@ int preproc_smem_bytes() { return (int)sizeof(Smem); }
 int launch_bodymask(const int16_t* vol, int S, int H, int W, int32_t* boxes, uint8_t* mask_out, int num_sms,
                     cudaStream_t stream) {
   if (H < 1 || W < 1 || H > 16384 || W > 16384) return -10;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_set_mask = 0ull;  // the dynamic shared-memory opt-in is a per-device function attribute
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
+  if (!((attr_set_mask >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(bodymask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
-    attr = true;
+    attr_set_mask |= 1ull << dev;
   }
   const int grid = S < num_sms ? S : num_sms;
   bodymask_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(vol, S, H, W, boxes, mask_out);
