@@ -1,7 +1,10 @@
 #!/bin/bash
-# Validation order for the paths that were prepared without GPU time.  Run under gpurun.
+# Validation order for the paths that were prepared without GPU time.  Run under gpurun,
+# after tools/build_probes.sh (here) and python -m lungmask_b200.build.
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
+# 0. the cta_group::2 conventions the pair kernel relies on (seconds; run tools/build_probes.sh locally first)
+timeout 60 tools/pair_probe > $O/pair_probe.log 2>&1; echo "pair_probe rc=$?"; cat $O/pair_probe.log
 # 1. CTA-pair convolution kernel: bit-exact integer checks first (layout / barrier mistakes), then float checks + timing
 timeout 180 tools/conv_probe 37 1 0 0 1 > $O/pair_probe_c1.log 2>&1; echo "pair probe rc=$?"
 grep -E "CHECK|TOTAL|timeout|error" $O/pair_probe_c1.log | cut -c1-200
