@@ -240,7 +240,7 @@ def run_engine(args):
                        "weights": "seeded synthetic state_dict, 60 Adam steps on phantoms (released .pth needs network)",
                        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
                        "mma_issuers_per_cta": 2 if os.environ.get("LM_DUAL_ISSUE", "0") not in ("", "0") else 1,
-                       "engine_env_options": {k: os.environ[k] for k in ("LM_CTA_PAIRS", "LM_STEM_V2", "LM_CCL_REDUCED", "LM_CHUNK_KB",
+                       "engine_env_options": {k: os.environ[k] for k in ("LM_CTA_PAIRS", "LM_STEM_V2", "LM_CCL_RULE", "LM_CHUNK_KB",
                                                                            "LM_CHUNK_KB_WIDE") if k in os.environ},
                        "e2e_matches_device_path": same},
             "e2e": {"value": e2e_value, "unit": "slices/s", "ms_per_step": e2e_ms,

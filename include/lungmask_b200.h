@@ -69,8 +69,16 @@ LM_API int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, in
 LM_API int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out);
 
 /* LMInferer.apply with a fill model, mask.py:223-232 (two inferences + spare-label fusion +
- * postprocessing(spare=[max+1]) at the original resolution). */
-LM_API int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out);
+ * postprocessing(spare=[max+1]) at the original resolution).  flags: LM_FLAG_NO_POSTPROCESS reaches the two inner
+ * _inference calls only (mask.py:191-194 honours volume_postprocessing there); the fusion post-processing of
+ * mask.py:232 is unconditional, exactly as in the reference. */
+LM_API int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, int flags,
+                          uint8_t* out);
+/* The fusion glue alone, mask.py:228-230: spare = res_l.max() + 1 (uint8 arithmetic); res_l[(res_l == 0) & (res_r > 0)]
+ * = spare; res_l[res_r == 0] = 0.  Host (S,H,W) uint8 in, fused (S,H,W) uint8 + the spare value out (parity tap: the
+ * array utils.postprocessing(res_l, spare=[spare]) receives at mask.py:232). */
+LM_API int lm_fuse(lm_engine* e, const uint8_t* res_l, const uint8_t* res_r, int S, int H, int W, uint8_t* fused,
+                   int* spare_value);
 
 /* ---- stage-level entry points (each mirrors one reference function; used by the parity tests) ---- */
 
@@ -112,7 +120,8 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * layers, 2 for the wide ones), "dual_issue" (0/1: a second MMA-issuing thread per CTA on alternate chunks;
  * default 0), "cta_pairs" (0/1: the experimental cta_group::2 convolution kernel; default 0),
  * "stem_v2" (0/1: the experimental register-resident stem kernel; default 0),
- * "ccl_reduced" (0/1: reduced neighbour set in the 26-connected labelling; default 0),
+ * "ccl_rule" (1 = pruned neighbour rule of the 26-connected labelling, the default; 0 = probe all 13 backward
+ * neighbours), "post_region_capacity" (test hook: size of the post-processing's region tables),
  * "post_debug_stage" (parity taps of the post-processing). */
 LM_API int lm_set_option(lm_engine* e, const char* key, int value);
 LM_API int lm_last_conv_timing(const lm_engine* e, float* conv_ms, int64_t* conv_launches);

@@ -38,7 +38,8 @@ def lib():
         "lm_load_weights": ([vp, i32, f32p, C.c_size_t, i32], i32),
         "lm_apply_volume": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_volume_dev": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
-        "lm_apply_fused": ([vp, i32, i32, i16p, i32, i32, i32, u8p], i32),
+        "lm_apply_fused": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
+        "lm_fuse": ([vp, u8p, u8p, i32, i32, i32, u8p, C.POINTER(i32)], i32),
         "lm_preprocess": ([vp, i16p, i32, i32, i32, i32, i32, i32, i16p, i32p], i32),
         "lm_simple_bodymask": ([vp, i16p, i32, i32, u8p], i32),
         "lm_forward": ([vp, i32, i16p, i32, u8p, f32p], i32),
@@ -60,7 +61,7 @@ def lib():
 
 
 EXPORTS = ["lm_create", "lm_destroy", "lm_last_error", "lm_device", "lm_batch_capacity", "lm_weight_blob_floats",
-           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_preprocess",
+           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_fuse", "lm_preprocess",
            "lm_simple_bodymask", "lm_forward", "lm_forward_dev", "lm_postprocess", "lm_reshape_masks",
            "lm_keep_largest_component",
            "lm_last_timings", "lm_set_option", "lm_last_conv_timing",
@@ -124,12 +125,26 @@ class Engine:
         _check(lib().lm_apply_volume_dev(self._h, slot, C.c_void_p(d_vol_ptr), S, H, W,
                                          0 if postprocess else FLAG_NO_POSTPROCESS, C.c_void_p(d_out_ptr)))
 
-    def apply_fused(self, slot_base, slot_fill, vol):
+    def apply_fused(self, slot_base, slot_fill, vol, postprocess=True):
+        """`postprocess` = LMInferer.volume_postprocessing: it reaches the two inner inferences only (mask.py:191-194);
+        the fusion post-processing (mask.py:232) always runs."""
         vol = _as(vol, np.int16, 3)
         out = np.empty(vol.shape, np.uint8)
         S, H, W = vol.shape
-        _check(lib().lm_apply_fused(self._h, slot_base, slot_fill, _ptr(vol), S, H, W, _ptr(out)))
+        _check(lib().lm_apply_fused(self._h, slot_base, slot_fill, _ptr(vol), S, H, W,
+                                    0 if postprocess else FLAG_NO_POSTPROCESS, _ptr(out)))
         return out
+
+    def fuse(self, res_l, res_r):
+        """mask.py:228-230 -> (fused uint8 volume before the post-processing, spare value)."""
+        res_l, res_r = _as(res_l, np.uint8, 3), _as(res_r, np.uint8, 3)
+        if res_l.shape != res_r.shape:
+            raise ValueError("fuse: shapes differ")
+        out = np.empty(res_l.shape, np.uint8)
+        spare = C.c_int(0)
+        S, H, W = res_l.shape
+        _check(lib().lm_fuse(self._h, _ptr(res_l), _ptr(res_r), S, H, W, _ptr(out), C.byref(spare)))
+        return out, int(spare.value)
 
     # ---- stages
     def preprocess(self, vol, out_h=NET_RES, out_w=NET_RES, clip=True):

@@ -136,6 +136,7 @@ struct lm_engine {
   int device = 0, B = 0, num_sms = 0;
   cudaStream_t st = nullptr;
   void* act[NUM_ACT] = {};  // split buffers: op_t planes; "L" buffers: fp32
+  int32_t* d_spare = nullptr;  // device int32[16]: spare label values computed on the device (fusion, mask.py:228)
   int* d_range = nullptr;   // device flag: a value left the operand format's range (fp16 build: |x| > 65504)
   int* h_range = nullptr;   // pinned host copy, refreshed at the end of every forward
   Slot slots[LM_MAX_SLOTS];
@@ -291,7 +292,9 @@ int inference_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, in
   CU(cudaEventRecord(e->ev[3], e->st));
   const uint8_t* masks = e->d_labels.p;
   if (!(flags & LM_FLAG_NO_POSTPROCESS)) {
-    RC(postprocess_device(e->post, e->d_labels.p, S, R, R, nullptr, 0, 3, e->d_post.p, e->num_sms, e->st, &e->launches));
+    // labels out of the argmax are < K: the post-processing needs no host round trip to learn which occur
+    RC(postprocess_device(e->post, e->d_labels.p, S, R, R, nullptr, 0, nullptr, 0, 3, e->slots[slot].K - 1, e->d_post.p, e->num_sms,
+                          e->st, &e->launches));
     masks = e->d_post.p;
   }
   CU(cudaEventRecord(e->ev[4], e->st));
@@ -310,6 +313,21 @@ int check_range(lm_engine* e) {
                      "(rebuild with -DLM_OPERAND_F16=0 for the tf32 operand format)");
   }
   return 0;
+}
+
+// Enqueue-synchronise-verify: `enqueue` puts a whole call on the engine stream; after the synchronisation the
+// post-processing reports whether its region tables were large enough (the region count lives on the device).  If not,
+// the tables grow to the reported size and the call is enqueued once more (a label map with more than one region per 32
+// voxels; never seen with a trained network).
+template <typename F>
+int run_checked(lm_engine* e, F&& enqueue) {
+  for (int attempt = 0;; ++attempt) {
+    RC(enqueue());
+    CU(cudaStreamSynchronize(e->st));
+    if (!postprocess_finish(e->post)) return 0;
+    if (attempt >= 2) return fail(-22, "post-processing: region tables overflowed repeatedly (%u regions)", e->post.last_regions);
+    RC(e->post.reserve_regions(e->post.want_regions));
+  }
 }
 
 void collect_timings(lm_engine* e) {
@@ -354,7 +372,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
   if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
-  if (const char* c = getenv("LM_CCL_REDUCED")) e->post.ccl_reduced = atoi(c) != 0;
+  if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
   CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&e->ev[i]));
@@ -364,6 +382,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
     const size_t elems = (size_t)batch_capacity * hw * hw * ACT[a].C;
     CU(cudaMalloc(&e->act[a], ACT[a].split ? elems * 2 * sizeof(op_t) : elems * sizeof(float)));
   }
+  CU(cudaMalloc(&e->d_spare, 16 * sizeof(int32_t)));
   CU(cudaMalloc(&e->d_range, sizeof(int)));
   CU(cudaMemset(e->d_range, 0, sizeof(int)));
   CU(cudaMallocHost(&e->h_range, sizeof(int)));
@@ -379,6 +398,7 @@ void lm_destroy(lm_engine* e) {
   cudaStreamSynchronize(e->st);
   for (int a = 0; a < NUM_ACT; ++a) cudaFree(e->act[a]);
   cudaFree(e->d_range);
+  cudaFree(e->d_spare);
   cudaFreeHost(e->h_range);
   for (auto& s : e->slots) {
     cudaFree(s.stem_w); cudaFree(s.stem_bias); cudaFree(s.stem_scale); cudaFree(s.stem_shift); cudaFree(s.head_w); cudaFree(s.head_b);
@@ -470,11 +490,14 @@ int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int
   if (!e || !d_vol || !d_out) return fail(-1, "lm_apply_volume_dev: NULL argument");
   if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_volume_dev: empty volume (%d,%d,%d)", S, H, W);
   CU(cudaSetDevice(e->device));
-  e->launches = 0;
-  CU(cudaEventRecord(e->ev[0], e->st));
-  RC(inference_dev(e, slot, d_vol, S, H, W, flags, d_out));
-  CU(cudaEventRecord(e->ev[6], e->st));
-  CU(cudaStreamSynchronize(e->st));
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    RC(inference_dev(e, slot, d_vol, S, H, W, flags, d_out));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
   collect_timings(e);
   return check_range(e);
 }
@@ -486,18 +509,21 @@ int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, in
   const size_t n = (size_t)S * H * W;
   RC(e->d_vol.reserve(n));
   RC(e->d_out.reserve(n));
-  e->launches = 0;
-  CU(cudaEventRecord(e->ev[0], e->st));
-  CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
-  RC(inference_dev(e, slot, e->d_vol.p, S, H, W, flags, e->d_out.p));
-  CU(cudaMemcpyAsync(out, e->d_out.p, n, cudaMemcpyDeviceToHost, e->st));
-  CU(cudaEventRecord(e->ev[6], e->st));
-  CU(cudaStreamSynchronize(e->st));
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+    RC(inference_dev(e, slot, e->d_vol.p, S, H, W, flags, e->d_out.p));
+    CU(cudaMemcpyAsync(out, e->d_out.p, n, cudaMemcpyDeviceToHost, e->st));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
   collect_timings(e);
   return check_range(e);
 }
 
-int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, uint8_t* out) {
+int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
   if (!e || !vol || !out) return fail(-1, "lm_apply_fused: NULL argument");
   if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_fused: empty volume");
   CU(cudaSetDevice(e->device));
@@ -505,21 +531,45 @@ int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vo
   RC(e->d_vol.reserve(n));
   RC(e->d_out.reserve(n));
   RC(e->d_out2.reserve(n));
-  e->launches = 0;
-  CU(cudaEventRecord(e->ev[0], e->st));
-  CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
-  RC(inference_dev(e, slot_base, e->d_vol.p, S, H, W, 0, e->d_out.p));   // res_l (mask.py:225)
-  RC(inference_dev(e, slot_fill, e->d_vol.p, S, H, W, 0, e->d_out2.p));  // res_r (mask.py:227)
-  int spare = 0;
-  RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, &spare, e->num_sms, e->st));
-  e->launches += 2;
-  const int32_t sp[1] = {spare};
-  RC(postprocess_device(e->post, e->d_out.p, S, H, W, sp, 1, 3, e->d_out2.p, e->num_sms, e->st, &e->launches));  // mask.py:232
-  CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
-  CU(cudaEventRecord(e->ev[6], e->st));
-  CU(cudaStreamSynchronize(e->st));
+  if (slot_base < 0 || slot_base >= LM_MAX_SLOTS || !e->slots[slot_base].loaded) return fail(-30, "weight slot %d not loaded", slot_base);
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+    // both inner inferences honour volume_postprocessing (mask.py:191-194); the fusion post-processing below does not
+    const int inner = flags & LM_FLAG_NO_POSTPROCESS;
+    RC(inference_dev(e, slot_base, e->d_vol.p, S, H, W, inner, e->d_out.p));   // res_l (mask.py:225)
+    RC(inference_dev(e, slot_fill, e->d_vol.p, S, H, W, inner, e->d_out2.p));  // res_r (mask.py:227)
+    RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, e->d_spare, e->num_sms, e->st));  // spare stays on the device
+    e->launches += 3;
+    // labels after the fusion are <= K_base (the spare value is max + 1 <= K_base): mask.py:232
+    RC(postprocess_device(e->post, e->d_out.p, S, H, W, nullptr, 0, e->d_spare, 1, 3, e->slots[slot_base].K, e->d_out2.p, e->num_sms,
+                          e->st, &e->launches));
+    CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
   collect_timings(e);
   return check_range(e);
+}
+
+int lm_fuse(lm_engine* e, const uint8_t* res_l, const uint8_t* res_r, int S, int H, int W, uint8_t* fused, int* spare_value) {
+  if (!e || !res_l || !res_r || !fused || !spare_value) return fail(-1, "lm_fuse: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_fuse: empty volume");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W;
+  RC(e->d_out.reserve(n));
+  RC(e->d_out2.reserve(n));
+  CU(cudaMemcpyAsync(e->d_out.p, res_l, n, cudaMemcpyHostToDevice, e->st));
+  CU(cudaMemcpyAsync(e->d_out2.p, res_r, n, cudaMemcpyHostToDevice, e->st));
+  RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, e->d_spare, e->num_sms, e->st));
+  CU(cudaMemcpyAsync(fused, e->d_out.p, n, cudaMemcpyDeviceToHost, e->st));
+  int32_t spare = 0;
+  CU(cudaMemcpyAsync(&spare, e->d_spare, sizeof(int32_t), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
+  *spare_value = (int)spare;
+  return 0;
 }
 
 int lm_preprocess(lm_engine* e, const int16_t* vol, int S, int H, int W, int out_h, int out_w, int clip,
@@ -586,12 +636,16 @@ int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, con
   const size_t n = (size_t)S * H * W;
   RC(e->d_out.reserve(n));
   RC(e->d_out2.reserve(n));
-  CU(cudaMemcpyAsync(e->d_out.p, labels, n, cudaMemcpyHostToDevice, e->st));
-  int64_t launches = 0;
-  RC(postprocess_device(e->post, e->d_out.p, S, H, W, spare, n_spare, skip_below, e->d_out2.p, e->num_sms, e->st, &launches));
-  CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
-  CU(cudaStreamSynchronize(e->st));
-  return 0;
+  if (n_spare < 0 || n_spare > 16 || (n_spare > 0 && !spare)) return fail(-1, "lm_postprocess: n_spare %d not in [0,16]", n_spare);
+  return run_checked(e, [&]() -> int {
+    CU(cudaMemcpyAsync(e->d_out.p, labels, n, cudaMemcpyHostToDevice, e->st));
+    int64_t launches = 0;
+    // arbitrary label values: the post-processing synchronises once to learn which occur (max_label = -1)
+    RC(postprocess_device(e->post, e->d_out.p, S, H, W, spare, n_spare, nullptr, 0, skip_below, -1, e->d_out2.p, e->num_sms, e->st,
+                          &launches));
+    CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
+    return 0;
+  });
 }
 
 int lm_keep_largest_component(lm_engine* e, const uint8_t* mask, int S, int H, int W, uint8_t* out) {
@@ -663,7 +717,15 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
   if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
-  if (!strcmp(key, "ccl_reduced")) { e->post.ccl_reduced = value != 0; return 0; }
+  if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
+  if (!strcmp(key, "post_region_capacity")) {  // test hook: shrink / grow the region tables (exercises the overflow re-run)
+    if (value < 1) return fail(-1, "post_region_capacity must be >= 1");
+    CU(cudaSetDevice(e->device));
+    CU(cudaStreamSynchronize(e->st));
+    e->post.release_regions();
+    if (e->post.cap_vox) RC(e->post.reserve_regions((uint32_t)value));
+    return 0;
+  }
   if (!strcmp(key, "chunk_kb_wide")) { if (value < 1) return fail(-1, "chunk_kb_wide must be >= 1"); e->chunk_kb_wide = value; return 0; }
   return fail(-1, "lm_set_option: unknown key %s", key);
 }

@@ -5,7 +5,9 @@
 //  Q1  26-connected components of equal label value: union-find over the voxel grid (roots = minimum linear
 //      index, so ranking the roots reproduces skimage's raster-order ids)               utils.py:293
 //  Q2  per region: area, label value, bounding box                                      utils.py:298
-//  Q3  stable sort by area + per-label "record" pass (host, O(R log R) on a few KB)     utils.py:299-308
+//  Q3  ascending (area, id) order by a bitonic sort of 64-bit keys + the per-label "record" pass restated
+//      order-free (a region sets a record iff it has the lowest id among the regions of its value AND area;
+//      the final record of a value is its largest area), all on device                   utils.py:299-308
 //  Q4  the order-dependent merge loop runs in ONE persistent CTA on the device: per candidate region it
 //      scans the region's (growing) bounding box, histograms the ids of the 6-connected ring voxels, picks
 //      the max-count / lowest-id neighbour and updates area / record / redirect tables   utils.py:310-339
@@ -13,6 +15,12 @@
 //  Q6  per label: largest 26-connected component, then holes (background not 6-connected to the border,
 //      or 2-D 4-connected background components < 64 px for single-slice volumes) filled, painted in
 //      ascending label order                                                            utils.py:344-358
+//
+// Round 2: the host is out of the loop.  The region count R, the sort, the records, the per-label boxes and the
+// "is this label present" decisions stay in device memory; kernels read them there (grids are sized for the volume,
+// loops for the device-side bounds).  With a known label bound the whole post-processing is enqueued without a single
+// host synchronisation (one when the bound is unknown); the region tables have a capacity and the device raises a
+// flag when R exceeds it (postprocess_finish -> the caller grows the tables and runs again).
 #include <algorithm>
 #include <vector>
 #include <string.h>
@@ -25,6 +33,19 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 
 struct Box { int z0, z1, y0, y1, x0, x1; };  // half-open
 struct Dim { int S, H, W; };
+// A box known on the host (dyn == nullptr) or the extent [z0,z1,y0,y1,x0,x1) in device memory grown by one voxel and
+// clipped (the analysis box of the hole filling); `gate` (optional) points to a device flag: 0 = the kernel has nothing to do.
+struct BoxSrc { Box fixed; const int* dyn; const uint32_t* gate; };
+
+__device__ __forceinline__ bool resolve_box(const BoxSrc& s, const Dim& d, Box& b) {
+  if (s.gate && *s.gate == 0u) return false;
+  if (!s.dyn) { b = s.fixed; return true; }
+  if (s.dyn[1] < 0) return false;  // empty extent
+  b.z0 = max(s.dyn[0] - 1, 0); b.z1 = min(s.dyn[1] + 1, d.S);
+  b.y0 = max(s.dyn[2] - 1, 0); b.y1 = min(s.dyn[3] + 1, d.H);
+  b.x0 = max(s.dyn[4] - 1, 0); b.x1 = min(s.dyn[5] + 1, d.W);
+  return true;
+}
 
 __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t i) {
   uint32_t p = parent[i];
@@ -61,49 +82,88 @@ __device__ __forceinline__ uint32_t box_voxel(const Box& b, const Dim& d, size_t
   return (uint32_t)(((size_t)z * d.H + y) * d.W + x);
 }
 
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, Box b) {
+// Union-find initialisation.  Consecutive threads hold consecutive voxels of a row, so the x-runs of equal label are
+// linked here without atomics: every voxel points at the first voxel of its run WITHIN the warp's 32-voxel segment
+// (a run start is the smallest index of the run: the min-index-root invariant holds); the merge kernel joins the
+// segments (lane 0 only).  All lanes run the same number of iterations (the ballot needs them).
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, BoxSrc bs) {
+  Box b;
+  if (!resolve_box(bs, d, b)) return;
   const size_t n = box_volume(b);
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-    int z, y, x;
-    const uint32_t i = box_voxel(b, d, t, z, y, x);
-    parent[i] = vals[i] ? i : NONE;
+  const unsigned lane = threadIdx.x & 31u;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t t0 = blockIdx.x * (size_t)blockDim.x + (threadIdx.x - lane); t0 < n; t0 += stride) {
+    const size_t t = t0 + lane;
+    uint32_t i = 0;
+    uint8_t v = 0;
+    bool left = false;
+    if (t < n) {
+      int z, y, x;
+      i = box_voxel(b, d, t, z, y, x);
+      v = vals[i];
+      left = v && lane > 0 && x > b.x0 && vals[i - 1] == v;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, left);
+    if (t < n) {
+      uint32_t p = NONE;
+      if (v) {
+        const unsigned stops = ~m & (0xffffffffu >> (31u - lane));  // lanes <= this one that start a run (lane 0 always does)
+        const unsigned start = 31u - (unsigned)__clz(stops);
+        p = i - (lane - start);
+      }
+      parent[i] = p;
+    }
   }
 }
 
 // CONN: 26 (3-D full), 6 (3-D faces), 4 (2-D faces within a slice). Only neighbours inside the box count.
-// reduced != 0 (CONN == 26 only; opt-in, lm_set_option("ccl_reduced")): when the left neighbour carries the same label
-// the voxel is united with it and with its four backward neighbours at dx = +1 only - the other eight backward
-// neighbours are backward neighbours of the left voxel, which unites with them itself.  Same partition, same
-// minimum-index roots (tests/test_ccl_neighbour_rule.py enumerates this on the CPU); 5 instead of 13 probes inside
-// homogeneous regions.
+// The x-runs are already linked inside every 32-voxel segment (ccl_init_kernel); here lane 0 joins the segments and each
+// voxel is united with its backward neighbours in the four rows (y-1,z), (y-1,z-1), (y,z-1), (y+1,z-1).
+// rule != 0 (CONN == 26; the default): per backward row with a = (x-1), b = (x), c = (x+1) of that row,
+//     b same label            -> unite with b, unless the left voxel carries the label too (it is united with b's row
+//                                through its own c or b, and b's row neighbours are linked by their own left links)
+//     b differs               -> unite with c if it matches; with a only if the left voxel does not carry the label
+// which performs no union at all inside homogeneous regions.  Same partition and same minimum-index roots as probing
+// all 13 backward neighbours (rule == 0): proof by induction along the row in DESIGN.md section 4.3; the CPU enumeration
+// is tests/test_ccl_neighbour_rule.py, the GPU comparison tests/test_gpu_stages.py::test_ccl_rules_agree.
 template <int CONN>
-__global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, Box b, int reduced) {
+__global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, BoxSrc bs, int rule) {
+  Box b;
+  if (!resolve_box(bs, d, b)) return;
   const size_t n = box_volume(b);
+  const size_t HW = (size_t)d.H * d.W;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
     const uint32_t i = box_voxel(b, d, t, z, y, x);
     const uint8_t v = vals[i];
     if (!v) continue;
-    const size_t HW = (size_t)d.H * d.W;
+    const bool left = x > b.x0 && vals[i - 1] == v;
+    if (left && (threadIdx.x & 31) == 0) uf_union(parent, i, i - 1);  // the run continues across a 32-voxel segment
     if (CONN == 26) {
-      const bool left = reduced && x > b.x0 && vals[i - 1] == v;
 #pragma unroll
-      for (int dz = -1; dz <= 0; ++dz)
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            if (dz == 0 && (dy > 0 || (dy == 0 && dx >= 0))) continue;  // backward half only
-            if (left && dx != 1 && !(dz == 0 && dy == 0 && dx == -1)) continue;  // covered by the left voxel
-            const int zz = z + dz, yy = y + dy, xx = x + dx;
-            if (zz < b.z0 || yy < b.y0 || yy >= b.y1 || xx < b.x0 || xx >= b.x1) continue;
-            const uint32_t j = (uint32_t)((size_t)zz * HW + (size_t)yy * d.W + xx);
-            if (vals[j] == v) uf_union(parent, i, j);
-          }
+      for (int r = 0; r < 4; ++r) {
+        const int dy = (r == 3) ? 1 : (r == 2 ? 0 : -1), dz = (r == 0) ? 0 : -1;
+        const int yy = y + dy, zz = z + dz;
+        if (zz < b.z0 || yy < b.y0 || yy >= b.y1) continue;
+        const uint32_t j = (uint32_t)((size_t)zz * HW + (size_t)yy * d.W + x);
+        const bool sb = vals[j] == v;
+        const bool sa = x > b.x0 && vals[j - 1] == v;
+        const bool sc = x + 1 < b.x1 && vals[j + 1] == v;
+        if (rule) {
+          if (sb) { if (!left) uf_union(parent, i, j); continue; }
+          if (sa && !left) uf_union(parent, i, j - 1);
+          if (sc) uf_union(parent, i, j + 1);
+        } else {
+          if (sa) uf_union(parent, i, j - 1);
+          if (sb) uf_union(parent, i, j);
+          if (sc) uf_union(parent, i, j + 1);
+        }
+      }
     } else {
-      if (x > b.x0 && vals[i - 1] == v) uf_union(parent, i, i - 1);
-      if (y > b.y0 && vals[i - d.W] == v) uf_union(parent, i, i - d.W);
-      if (CONN == 6 && z > b.z0 && vals[i - HW] == v) uf_union(parent, i, (uint32_t)(i - HW));
+      // faces only: the upper / previous-slice neighbour needs no union when the left voxel and ITS upper neighbour
+      // carry the label as well (left link + the neighbour's own left link close the square)
+      if (y > b.y0 && vals[i - d.W] == v && !(left && vals[i - d.W - 1] == v)) uf_union(parent, i, i - d.W);
+      if (CONN == 6 && z > b.z0 && vals[i - HW] == v && !(left && vals[i - HW - 1] == v)) uf_union(parent, i, (uint32_t)(i - HW));
     }
   }
 }
@@ -115,7 +175,9 @@ __device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t 
   while (p != i) { i = p; p = parent[i]; }
   return i;
 }
-__global__ void ccl_flatten_kernel(uint32_t* __restrict__ parent, Dim d, Box b) {
+__global__ void ccl_flatten_kernel(uint32_t* __restrict__ parent, Dim d, BoxSrc bs) {
+  Box b;
+  if (!resolve_box(bs, d, b)) return;
   const size_t n = box_volume(b);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
@@ -202,16 +264,79 @@ __global__ void __launch_bounds__(SCAN_BLOCK) roots_assign_kernel(const uint32_t
   }
 }
 
+// ---- small device tables (PostScratch::small, 32 KB) ----------------------------------------------------------
+// words: [0] largest R since the host last looked  [1] region-table overflow flag (sticky until then)
+//        [2] first present label value  [3] "label active" gate of the Q6 loop  [4] R of this run
+//        [8..264) present[256]  [512..768) record[256] (origlabels_maxsub)
+// bytes: [4096..4352) spare_value[256]   [8192..10240) best root per label value (u64[256])
+//        [16384..16408) extent of the label being finalised (int[6])   [16640..) spare label values (int32[16])
+constexpr int W_MAXR = 0, W_OVERFLOW = 1, W_FIRST = 2, W_GATE = 3, W_R = 4, W_PRESENT = 8, W_RECORD = 512;
+constexpr int B_SPARE_VALUE = 4096, B_BEST = 8192, B_BBOX1 = 16384, B_SPARE_LIST = 16640;
+constexpr int MAX_SPARE = 16;
+
+struct SpareArgs { int n; int v[MAX_SPARE]; const int32_t* d_extra; int n_extra; };
+
+// spare tables + record / present / best reset (one block)
+__global__ void post_setup_kernel(uint32_t* __restrict__ small, SpareArgs sp, int clear_sticky) {
+  uint8_t* spare_value = reinterpret_cast<uint8_t*>(small) + B_SPARE_VALUE;
+  int32_t* spare_list = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(small) + B_SPARE_LIST);
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(small) + B_BEST);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    spare_value[i] = 0;
+    small[W_PRESENT + i] = 0;
+    small[W_RECORD + i] = 0;
+    best[i] = 0ull;
+  }
+  if (threadIdx.x == 0) {
+    small[W_GATE] = 0; small[W_FIRST] = 0;
+    if (clear_sticky) { small[W_OVERFLOW] = 0; small[W_MAXR] = 0; }
+  }
+  __syncthreads();
+  const int total = sp.n + sp.n_extra;
+  for (int i = threadIdx.x; i < MAX_SPARE; i += blockDim.x) {
+    int v = -1;
+    if (i < sp.n) v = sp.v[i];
+    else if (i < total) v = sp.d_extra[i - sp.n];
+    spare_list[i] = v;
+    if (v >= 0 && v < 256) spare_value[v] = 1;
+  }
+}
+
+// region tables for ids 0..min(R, cap): zero / identity, spare_id[i] = "the ID i equals a spare entry" (utils.py:322)
+__global__ void region_init_kernel(uint32_t* __restrict__ small, uint32_t cap, uint32_t* __restrict__ area,
+                                   uint32_t* __restrict__ count, uint8_t* __restrict__ value, int* __restrict__ bbox,
+                                   uint32_t* __restrict__ cur, uint8_t* __restrict__ to_label, uint8_t* __restrict__ spare_id) {
+  const uint32_t R = small[W_R];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicMax(&small[W_MAXR], R);
+    if (R > cap) small[W_OVERFLOW] = 1;
+  }
+  const uint32_t top = R < cap ? R : cap;
+  const int32_t* spare_list = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(small) + B_SPARE_LIST);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= top; i += gridDim.x * blockDim.x) {
+    area[i] = 0; count[i] = 0; value[i] = 0; cur[i] = i; to_label[i] = 0;
+    int* b = bbox + 6 * (size_t)i;
+    b[0] = b[2] = b[4] = 1 << 30;
+    b[1] = b[3] = b[5] = -1;
+    uint8_t s = 0;
+#pragma unroll
+    for (int k = 0; k < MAX_SPARE; ++k) s |= (spare_list[k] >= 0 && (uint32_t)spare_list[k] == i) ? 1 : 0;
+    spare_id[i] = s;
+  }
+}
+
 // rid for every voxel (0 = background) + region statistics
 __global__ void region_stats_kernel(const uint8_t* __restrict__ vals, const uint32_t* __restrict__ parent,
-                                    uint32_t* __restrict__ rid, Dim d, uint32_t* __restrict__ area,
+                                    uint32_t* __restrict__ rid, Dim d, uint32_t cap, uint32_t* __restrict__ area,
                                     uint8_t* __restrict__ value, int* __restrict__ bbox) {
   const size_t n = (size_t)d.S * d.H * d.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t p = parent[i];
     if (p == NONE) { rid[i] = 0; continue; }
     const uint32_t id = rid[p];  // roots were assigned by roots_assign_kernel; non-roots never alias a root slot
-    if (p != (uint32_t)i) rid[i] = id; else value[id] = vals[i];
+    if (p != (uint32_t)i) rid[i] = id;
+    if (id > cap) continue;      // table overflow: flagged by region_init_kernel, the caller runs again with larger tables
+    if (p == (uint32_t)i) value[id] = vals[i];
     // warp-aggregated area count
     const unsigned peers = __match_any_sync(__activemask(), id);
     if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&area[id], (uint32_t)__popc(peers));
@@ -225,12 +350,82 @@ __global__ void region_stats_kernel(const uint8_t* __restrict__ vals, const uint
     if (x + 1 > bb[5]) atomicMax(&bb[5], x + 1);
   }
 }
-__global__ void bbox_init_kernel(int* __restrict__ bbox, uint32_t R) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= R; i += gridDim.x * blockDim.x) {
-    int* b = bbox + 6 * (size_t)i;
-    b[0] = b[2] = b[4] = 1 << 30;
-    b[1] = b[3] = b[5] = -1;
+
+// ---- Q2/Q3 on device ---------------------------------------------------------------------------------------
+// order[k] = id of the k-th region in ascending (area, id) order (Python's stable sort of the id-ordered list,
+// utils.py:299-300): bitonic sort of the keys area << 32 | id by ONE CTA - in shared memory up to 4096 regions, in
+// global memory above (R is a device-side value; a clean label map has tens of regions, a speckled one thousands).
+constexpr int SORT_SMEM = 4096;
+__device__ __forceinline__ void bitonic_pass(unsigned long long* keys, uint32_t npad, uint32_t k, uint32_t j) {
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x) {
+    const uint32_t l = i ^ j;
+    if (l > i) {
+      const unsigned long long a = keys[i], b = keys[l];
+      const bool up = (i & k) == 0;
+      if ((a > b) == up) { keys[i] = b; keys[l] = a; }
+    }
   }
+}
+__global__ void __launch_bounds__(1024, 1) region_sort_kernel(const uint32_t* __restrict__ small, uint32_t cap,
+                                                              const uint32_t* __restrict__ area,
+                                                              unsigned long long* __restrict__ gkeys,
+                                                              uint32_t* __restrict__ order) {
+  __shared__ unsigned long long skeys[SORT_SMEM];
+  const uint32_t R = small[W_R] < cap ? small[W_R] : cap;
+  if (R == 0) return;
+  uint32_t npad = 2;
+  while (npad < R) npad <<= 1;
+  unsigned long long* keys = npad <= SORT_SMEM ? skeys : gkeys;
+  for (uint32_t i = threadIdx.x; i < npad; i += blockDim.x)
+    keys[i] = i < R ? (((unsigned long long)area[i + 1] << 32) | (unsigned long long)(i + 1)) : ~0ull;
+  __syncthreads();
+  for (uint32_t k = 2; k <= npad; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      bitonic_pass(keys, npad, k, j);
+      __syncthreads();
+    }
+  for (uint32_t i = threadIdx.x; i < R; i += blockDim.x) order[i] = (uint32_t)(keys[i] & 0xFFFFFFFFull);
+}
+
+// Records (utils.py:303-308) without walking the sorted list: going through the regions in ascending (area, id) order,
+// a region sets a new record for its label value v iff its area is strictly larger than every earlier region of value
+// v, i.e. iff no region of value v with the SAME area has a lower id; the record left at the end is the largest area of
+// value v.  (area, v) -> lowest id through an open-addressing table.
+__device__ __forceinline__ uint32_t hash40(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+__global__ void record_insert_kernel(uint32_t* __restrict__ small, uint32_t cap, const uint32_t* __restrict__ area,
+                                     const uint8_t* __restrict__ value, unsigned long long* __restrict__ hkeys,
+                                     uint32_t* __restrict__ hmin, uint32_t hmask, uint32_t* __restrict__ hslot) {
+  __shared__ uint32_t srec[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) srec[i] = 0;
+  __syncthreads();
+  const uint32_t R = small[W_R] < cap ? small[W_R] : cap;
+  for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= R; id += gridDim.x * blockDim.x) {
+    const uint32_t a = area[id];
+    const uint8_t v = value[id];
+    atomicMax(&srec[v], a);
+    const unsigned long long key = ((unsigned long long)a << 8) | v;
+    uint32_t s = hash40(key) & hmask;
+    while (true) {
+      const unsigned long long prev = atomicCAS(&hkeys[s], ~0ull, key);
+      if (prev == ~0ull || prev == key) break;
+      s = (s + 1) & hmask;
+    }
+    atomicMin(&hmin[s], id);
+    hslot[id] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    if (srec[i]) atomicMax(&small[W_RECORD + i], srec[i]);
+}
+__global__ void record_lookup_kernel(const uint32_t* __restrict__ small, uint32_t cap, const uint8_t* __restrict__ value,
+                                     const uint32_t* __restrict__ hmin, const uint32_t* __restrict__ hslot,
+                                     uint8_t* __restrict__ to_label) {
+  const uint32_t R = small[W_R] < cap ? small[W_R] : cap;
+  for (uint32_t id = 1 + blockIdx.x * blockDim.x + threadIdx.x; id <= R; id += gridDim.x * blockDim.x)
+    to_label[id] = (hmin[hslot[id]] == id) ? value[id] : 0;
 }
 
 // ---- Q4: the sequential merge loop, one persistent CTA ---------------------------------------------------
@@ -257,7 +452,8 @@ struct MergeArgs {
   uint32_t* touched;       // [R+1] scratch
   const uint8_t* spare_value;  // [256] 1 where the label VALUE is spare            (utils.py:313: v in spare)
   const uint8_t* spare_id;     // [R+1] 1 where the region ID equals a spare entry  (utils.py:322: n not in spare)
-  uint32_t R;
+  const uint32_t* d_R;     // device-side region count
+  uint32_t cap;            // table capacity (ids above it do not exist in the tables)
   int skip_below;
   Dim d;
 };
@@ -270,13 +466,14 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
   const int tid = threadIdx.x;
   const Dim d = a.d;
   const size_t HW = (size_t)d.H * d.W;
+  const uint32_t R = *a.d_R < a.cap ? *a.d_R : a.cap;
   uint32_t k = 0;
-  while (k < a.R) {
+  while (k < R) {
     // The tables only change when a candidate is processed, so the next candidate can be searched for
     // 1024 regions at a time; the first hit (in list order) is the one the sequential loop would take.
     if (tid == 0) s_first = NONE;
     __syncthreads();
-    if (k + tid < a.R) {
+    if (k + tid < R) {
       const uint32_t rr = a.order[k + tid];
       const uint32_t ar = a.area[rr];
       const uint8_t v = a.value[rr];
@@ -302,16 +499,16 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
       int z, y, x;
       const uint32_t i = box_voxel(b, d, t, z, y, x);
       const uint32_t o = a.rid[i];
-      if (o == 0) continue;  // n != 0
+      if (o == 0 || o > a.cap) continue;  // n != 0 (ids beyond the tables exist only in an overflowed run, which is repeated)
       const uint32_t id = cur_find(a.cur, o);
       if (id == r) continue;  // n != r.label
       bool ring = false;  // binary_dilation(sub == r.label), 6-connected cross (utils.py:316)
-      if (x > 0)       { const uint32_t q = a.rid[i - 1];        ring |= (q && cur_find(a.cur, q) == r); }
-      if (x < d.W - 1) { const uint32_t q = a.rid[i + 1];        ring |= (q && cur_find(a.cur, q) == r); }
-      if (y > 0)       { const uint32_t q = a.rid[i - d.W];      ring |= (q && cur_find(a.cur, q) == r); }
-      if (y < d.H - 1) { const uint32_t q = a.rid[i + d.W];      ring |= (q && cur_find(a.cur, q) == r); }
-      if (z > 0)       { const uint32_t q = a.rid[i - HW];       ring |= (q && cur_find(a.cur, q) == r); }
-      if (z < d.S - 1) { const uint32_t q = a.rid[i + HW];       ring |= (q && cur_find(a.cur, q) == r); }
+      if (x > 0)       { const uint32_t q = a.rid[i - 1];        ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+      if (x < d.W - 1) { const uint32_t q = a.rid[i + 1];        ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+      if (y > 0)       { const uint32_t q = a.rid[i - d.W];      ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+      if (y < d.H - 1) { const uint32_t q = a.rid[i + d.W];      ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+      if (z > 0)       { const uint32_t q = a.rid[i - HW];       ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+      if (z < d.S - 1) { const uint32_t q = a.rid[i + HW];       ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
       if (!ring) continue;
       if (atomicAdd(&a.count[id], 1u) == 0u) a.touched[atomicAdd(&s_ntouched, 1u)] = id;
     }
@@ -349,11 +546,11 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
 // ---- Q5 -----------------------------------------------------------------------------------------------------
 __global__ void map_labels_kernel(const uint32_t* __restrict__ rid, uint32_t* __restrict__ cur,
                                   const uint8_t* __restrict__ to_label, const uint8_t* __restrict__ spare_value,
-                                  uint8_t* __restrict__ mapped, size_t n, uint32_t* __restrict__ present) {
+                                  uint8_t* __restrict__ mapped, size_t n, uint32_t* __restrict__ present, uint32_t cap) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t o = rid[i];
     uint8_t v = 0;
-    if (o) {
+    if (o && o <= cap) {
       v = to_label[cur_find(cur, o)];
       if (spare_value[v]) v = 0;
     }
@@ -363,10 +560,10 @@ __global__ void map_labels_kernel(const uint32_t* __restrict__ rid, uint32_t* __
 }
 
 __global__ void debug_ids_kernel(const uint32_t* __restrict__ rid, uint32_t* __restrict__ cur, uint8_t* __restrict__ out,
-                                 size_t n, int merged) {
+                                 size_t n, int merged, uint32_t cap) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint32_t o = rid[i];
-    if (o && merged) o = cur_find(cur, o);
+    if (o && o <= cap && merged) o = cur_find(cur, o);
     out[i] = (uint8_t)(o & 255u);
   }
 }
@@ -388,10 +585,30 @@ __global__ void best_root_kernel(const uint8_t* __restrict__ vals, const uint32_
     atomicMax(&best[vals[i]], ((unsigned long long)area[i] << 32) | (unsigned long long)(uint32_t)i);
   }
 }
-// keep mask of one label's largest component -> tmp = 1 where NOT kept (the "background" to analyse), and bbox
+// np.unique(outmask_mapped)[1:] (utils.py:355): the smallest label value present is skipped, whatever it is
+__global__ void first_present_kernel(uint32_t* __restrict__ small) {
+  if (threadIdx.x == 0) {
+    uint32_t f = 256;
+    for (int v = 255; v >= 0; --v) if (small[W_PRESENT + v]) f = (uint32_t)v;
+    small[W_FIRST] = f;
+  }
+}
+// opens the finalisation of label `v`: gate = present and not the first value; resets the extent
+__global__ void label_begin_kernel(uint32_t* __restrict__ small, int v) {
+  if (threadIdx.x == 0) {
+    small[W_GATE] = (small[W_PRESENT + v] && small[W_FIRST] != (uint32_t)v) ? 1u : 0u;
+    int* bb = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(small) + B_BBOX1);
+    bb[0] = bb[2] = bb[4] = 1 << 30;
+    bb[1] = bb[3] = bb[5] = -1;
+  }
+}
+// keep mask of one label's largest component -> tmp = 1 where NOT kept (the "background" to analyse), and its extent
 __global__ void keep_complement_kernel(const uint8_t* __restrict__ mapped, const uint32_t* __restrict__ parent,
-                                       uint8_t label, uint32_t root, uint8_t* __restrict__ tmp, Dim d,
-                                       int* __restrict__ bbox) {
+                                       uint8_t label, const unsigned long long* __restrict__ best,
+                                       uint8_t* __restrict__ tmp, Dim d, int* __restrict__ bbox,
+                                       const uint32_t* __restrict__ gate) {
+  if (*gate == 0u) return;
+  const uint32_t root = (uint32_t)(best[label] & 0xFFFFFFFFull);
   const size_t n = (size_t)d.S * d.H * d.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const bool keep = mapped[i] == label && parent[i] == root;
@@ -408,7 +625,9 @@ __global__ void keep_complement_kernel(const uint8_t* __restrict__ mapped, const
   }
 }
 // complement voxels on the faces of the analysis box are connected to the outside: flag their roots
-__global__ void seed_outside_kernel(const uint32_t* __restrict__ parent2, uint8_t* __restrict__ outside, Dim d, Box b) {
+__global__ void seed_outside_kernel(const uint32_t* __restrict__ parent2, uint8_t* __restrict__ outside, Dim d, BoxSrc bs) {
+  Box b;
+  if (!resolve_box(bs, d, b)) return;
   const size_t n = box_volume(b);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
@@ -418,7 +637,9 @@ __global__ void seed_outside_kernel(const uint32_t* __restrict__ parent2, uint8_
   }
 }
 __global__ void paint_filled_kernel(const uint32_t* __restrict__ parent2, const uint8_t* __restrict__ outside,
-                                    uint8_t label, uint8_t* __restrict__ out, Dim d, Box b) {
+                                    uint8_t label, uint8_t* __restrict__ out, Dim d, BoxSrc bs) {
+  Box b;
+  if (!resolve_box(bs, d, b)) return;
   const size_t n = box_volume(b);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
@@ -429,13 +650,31 @@ __global__ void paint_filled_kernel(const uint32_t* __restrict__ parent2, const 
 }
 // single-slice volumes: area_closing(area_threshold=64): 4-connected background components < 64 px are filled
 __global__ void paint_area_closing_kernel(const uint32_t* __restrict__ parent2, const uint32_t* __restrict__ area,
-                                          uint8_t label, uint8_t* __restrict__ out, size_t n, uint32_t threshold) {
+                                          uint8_t label, uint8_t* __restrict__ out, size_t n, uint32_t threshold,
+                                          const uint32_t* __restrict__ gate) {
+  if (*gate == 0u) return;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const uint32_t p = parent2[i];
     if (p == NONE || area[p] < threshold) out[i] = label;
   }
 }
-__global__ void clear_outside_kernel(const uint32_t* __restrict__ parent2, uint8_t* __restrict__ outside, Dim d, Box b) {
+__global__ void gated_zero_kernel(uint32_t* __restrict__ a, size_t n, const uint32_t* __restrict__ gate) {
+  if (*gate == 0u) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = 0;
+}
+__global__ void gated_root_area_kernel(const uint32_t* __restrict__ parent, uint32_t* __restrict__ area, size_t n,
+                                       const uint32_t* __restrict__ gate) {
+  if (*gate == 0u) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t p = parent[i];
+    if (p == NONE) continue;
+    const unsigned peers = __match_any_sync(__activemask(), p);
+    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&area[p], (uint32_t)__popc(peers));
+  }
+}
+__global__ void clear_outside_kernel(uint8_t* __restrict__ outside, Dim d, BoxSrc bs) {
+  Box b;
+  if (!resolve_box(bs, d, b)) return;
   const size_t n = box_volume(b);
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
     int z, y, x;
@@ -474,7 +713,13 @@ __global__ void max_u8_kernel(const uint8_t* __restrict__ a, size_t n, uint32_t*
   for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m) atomicMax(mx, m);
 }
-__global__ void fuse_kernel(uint8_t* __restrict__ res_l, const uint8_t* __restrict__ res_r, size_t n, uint8_t spare) {
+// spare = res_l.max() + 1 in uint8 arithmetic (mask.py:228), left in device memory for the post-processing
+__global__ void spare_from_max_kernel(const uint32_t* __restrict__ mx, int32_t* __restrict__ spare) {
+  if (threadIdx.x == 0) spare[0] = (int32_t)((mx[0] + 1u) & 0xFFu);
+}
+__global__ void fuse_kernel(uint8_t* __restrict__ res_l, const uint8_t* __restrict__ res_r, size_t n,
+                            const int32_t* __restrict__ spare_p) {
+  const uint8_t spare = (uint8_t)spare_p[0];
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint8_t l = res_l[i];
     const uint8_t r = res_r[i];
@@ -496,15 +741,24 @@ inline int grid_for(size_t n, int block, int num_sms) {
     if (e_ != cudaSuccess) return (int)e_; \
   } while (0)
 
+inline BoxSrc fixed_box(const Box& b) { BoxSrc s; s.fixed = b; s.dyn = nullptr; s.gate = nullptr; return s; }
+
+// n_hint: voxels the box can hold at most (grid sizing; the kernels loop over the box they resolve on the device)
 template <int CONN>
-int run_ccl(const uint8_t* vals, uint32_t* parent, Dim d, Box b, int num_sms, cudaStream_t st, int64_t* launches, int reduced = 0) {
-  const size_t n = (size_t)(b.z1 - b.z0) * (b.y1 - b.y0) * (b.x1 - b.x0);
-  const int g = grid_for(n, 256, num_sms);
-  ccl_init_kernel<<<g, 256, 0, st>>>(vals, parent, d, b);
-  ccl_merge_kernel<CONN><<<g, 256, 0, st>>>(vals, parent, d, b, reduced);
-  ccl_flatten_kernel<<<g, 256, 0, st>>>(parent, d, b);
+int run_ccl(const uint8_t* vals, uint32_t* parent, Dim d, const BoxSrc& bs, size_t n_hint, int num_sms, cudaStream_t st,
+            int64_t* launches, int rule = 1) {
+  const int g = grid_for(n_hint, 256, num_sms);   // init and merge MUST share the launch shape (32-voxel segments)
+  ccl_init_kernel<<<g, 256, 0, st>>>(vals, parent, d, bs);
+  ccl_merge_kernel<CONN><<<g, 256, 0, st>>>(vals, parent, d, bs, rule);
+  ccl_flatten_kernel<<<g, 256, 0, st>>>(parent, d, bs);
   *launches += 3;
   return (int)cudaGetLastError();
+}
+
+uint32_t pow2_at_least(uint64_t x) {
+  uint64_t p = 2;
+  while (p < x) p <<= 1;
+  return (uint32_t)p;
 }
 
 }  // namespace
@@ -513,34 +767,41 @@ int run_ccl(const uint8_t* vals, uint32_t* parent, Dim d, Box b, int num_sms, cu
 int PostScratch::reserve(size_t nvox) {
   if (nvox <= cap_vox) return 0;
   release();
-  cap_vox = nvox;
   const size_t nb = (nvox + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS);
-  LM_CUDA(cudaMalloc(&parent, nvox * 4));
-  LM_CUDA(cudaMalloc(&parent2, nvox * 4));
-  LM_CUDA(cudaMalloc(&rid, nvox * 4));
-  LM_CUDA(cudaMalloc(&area2, nvox * 4));
-  LM_CUDA(cudaMalloc(&mapped, nvox));
-  LM_CUDA(cudaMalloc(&tmp, nvox));
-  LM_CUDA(cudaMalloc(&outside, nvox));
-  LM_CUDA(cudaMalloc(&block_counts, (nb + 1) * 4));
-  LM_CUDA(cudaMalloc(&small, 4096 * 8));
-  LM_CUDA(cudaMallocHost(&h_small, 4096 * 8));
-  return 0;
+  int rc = 0;
+  auto A = [&](void* pp, size_t bytes) { if (!rc) { cudaError_t e = cudaMalloc((void**)pp, bytes); if (e != cudaSuccess) rc = (int)e; } };
+  A(&parent, nvox * 4); A(&parent2, nvox * 4); A(&rid, nvox * 4); A(&area2, nvox * 4);
+  A(&mapped, nvox); A(&tmp, nvox); A(&outside, nvox);
+  A(&block_counts, (nb + 1) * 4); A(&small, 4096 * 8);
+  if (!rc) { cudaError_t e = cudaMallocHost((void**)&h_small, 4096 * 8); if (e != cudaSuccess) rc = (int)e; }
+  if (!rc) { cudaError_t e = cudaMemset(outside, 0, nvox); if (e != cudaSuccess) rc = (int)e; }  // kept all-zero between uses
+  if (rc) { release(); return rc; }  // capacities stay 0: the next call allocates again instead of using dangling pointers
+  cap_vox = nvox;
+  // region tables: sized for a speckled label map (1 region per 32 voxels); a map with more regions overflows once, the
+  // device reports the count and the caller retries with tables of that size
+  const uint64_t want = nvox / 32 > 65536 ? nvox / 32 : 65536;
+  return reserve_regions((uint32_t)(want < nvox ? want : nvox));
+}
+void PostScratch::release_regions() {
+  cudaFree(r_area); cudaFree(r_value); cudaFree(r_bbox); cudaFree(r_cur); cudaFree(r_order); cudaFree(r_count);
+  cudaFree(r_touched); cudaFree(r_spare_id); cudaFree(r_to_label); cudaFree(r_hslot); cudaFree(sort_keys);
+  cudaFree(hash_keys); cudaFree(hash_min); cudaFree(batch);
+  r_area = r_cur = r_order = r_count = r_touched = r_hslot = nullptr; r_value = r_spare_id = r_to_label = nullptr; r_bbox = nullptr;
+  sort_keys = hash_keys = nullptr; hash_min = nullptr; batch = nullptr;
+  cap_regions = 0; hash_cap = 0; sort_cap = 0;
 }
 int PostScratch::reserve_regions(uint32_t R) {
-  if (R + 1 <= cap_regions) return 0;
-  cudaFree(r_area); cudaFree(r_value); cudaFree(r_bbox); cudaFree(r_cur); cudaFree(r_order); cudaFree(r_count);
-  cudaFree(r_touched); cudaFree(r_spare_id); cudaFree(r_to_label);
-  cap_regions = (size_t)(R + 1) * 2;
-  LM_CUDA(cudaMalloc(&r_area, cap_regions * 4));
-  LM_CUDA(cudaMalloc(&r_value, cap_regions));
-  LM_CUDA(cudaMalloc(&r_bbox, cap_regions * 6 * 4));
-  LM_CUDA(cudaMalloc(&r_cur, cap_regions * 4));
-  LM_CUDA(cudaMalloc(&r_order, cap_regions * 4));
-  LM_CUDA(cudaMalloc(&r_count, cap_regions * 4));
-  LM_CUDA(cudaMalloc(&r_touched, cap_regions * 4));
-  LM_CUDA(cudaMalloc(&r_spare_id, cap_regions));
-  LM_CUDA(cudaMalloc(&r_to_label, cap_regions));
+  if (R <= cap_regions && cap_regions) return 0;
+  release_regions();
+  const size_t c = (size_t)R + 1;
+  const uint32_t hc = pow2_at_least(2 * (uint64_t)c), sc = pow2_at_least(c);
+  int rc = 0;
+  auto A = [&](void* pp, size_t bytes) { if (!rc) { cudaError_t e = cudaMalloc((void**)pp, bytes); if (e != cudaSuccess) rc = (int)e; } };
+  A(&r_area, c * 4); A(&r_value, c); A(&r_bbox, c * 6 * 4); A(&r_cur, c * 4); A(&r_order, c * 4); A(&r_count, c * 4);
+  A(&r_touched, c * 4); A(&r_spare_id, c); A(&r_to_label, c); A(&r_hslot, c * 4);
+  A(&sort_keys, (size_t)sc * 8); A(&hash_keys, (size_t)hc * 8); A(&hash_min, (size_t)hc * 4);
+  if (rc) { release_regions(); return rc; }
+  cap_regions = R; hash_cap = hc; sort_cap = sc;
   return 0;
 }
 void PostScratch::release() {
@@ -548,161 +809,142 @@ void PostScratch::release() {
   cudaFree(block_counts); cudaFree(small);
   if (h_small) cudaFreeHost(h_small);
   parent = parent2 = rid = area2 = nullptr; mapped = tmp = outside = nullptr; block_counts = nullptr; small = nullptr; h_small = nullptr;
-  cudaFree(r_area); cudaFree(r_value); cudaFree(r_bbox); cudaFree(r_cur); cudaFree(r_order); cudaFree(r_count);
-  cudaFree(r_touched); cudaFree(r_spare_id); cudaFree(r_to_label);
-  r_area = r_cur = r_order = r_count = r_touched = nullptr; r_value = r_spare_id = r_to_label = nullptr; r_bbox = nullptr;
-  cap_vox = 0; cap_regions = 0;
+  release_regions();
+  cap_vox = 0;
 }
 
 int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, int W, const int32_t* spare, int n_spare,
-                       int skip_below, uint8_t* d_out, int num_sms, cudaStream_t st, int64_t* launches) {
+                       const int32_t* d_spare, int n_d_spare, int skip_below, int max_label, uint8_t* d_out, int num_sms,
+                       cudaStream_t st, int64_t* launches) {
   const size_t n = (size_t)S * H * W;
   if (n == 0) return 0;
   if (n >= 0xFFFFFFF0ull) return -20;
+  if (n_spare < 0 || n_d_spare < 0 || n_spare + n_d_spare > MAX_SPARE) return -23;
   int rc = ws.reserve(n);
   if (rc) return rc;
   const Dim d{S, H, W};
   const Box full{0, S, 0, H, 0, W};
+  const BoxSrc fullsrc = fixed_box(full);
   const int g = grid_for(n, 256, num_sms);
-  uint32_t* d_small = reinterpret_cast<uint32_t*>(ws.small);  // [0] R, [8..264) present flags, [512..1024) record etc.
+  uint32_t* d_small = reinterpret_cast<uint32_t*>(ws.small);
+  uint8_t* small_b = reinterpret_cast<uint8_t*>(ws.small);
+  uint32_t* d_record = d_small + W_RECORD;
+  uint32_t* d_present = d_small + W_PRESENT;
+  const uint32_t* d_gate = d_small + W_GATE;
+  uint8_t* d_spare_value = small_b + B_SPARE_VALUE;
+  unsigned long long* d_best = reinterpret_cast<unsigned long long*>(small_b + B_BEST);
+  int* d_bbox1 = reinterpret_cast<int*>(small_b + B_BBOX1);
+  const uint32_t cap = ws.cap_regions;
+  ws.want_regions = 0;
 
-  // Q1: components + canonical ids
-  rc = run_ccl<26>(d_labels, ws.parent, d, full, num_sms, st, launches, ws.ccl_reduced);
+  SpareArgs sp{};
+  sp.n = n_spare;
+  for (int i = 0; i < n_spare; ++i) sp.v[i] = spare[i];
+  sp.d_extra = d_spare; sp.n_extra = n_d_spare;
+  post_setup_kernel<<<1, 256, 0, st>>>(d_small, sp, ws.clear_sticky ? 1 : 0);
+  ws.clear_sticky = false;
+
+  // Q1: components + canonical ids (R stays on the device: d_small[W_R])
+  rc = run_ccl<26>(d_labels, ws.parent, d, fullsrc, n, num_sms, st, launches, ws.ccl_rule);
   if (rc) return rc;
   const int nb = (int)((n + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS));
   roots_count_kernel<<<nb, SCAN_BLOCK, 0, st>>>(ws.parent, n, ws.block_counts);
-  scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.block_counts, nb, d_small);
+  scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.block_counts, nb, d_small + W_R);
   roots_assign_kernel<<<nb, SCAN_BLOCK, 0, st>>>(ws.parent, n, ws.block_counts, ws.rid);
-  *launches += 3;
-  uint32_t R = 0;
-  LM_CUDA(cudaMemcpyAsync(&ws.h_small[0], d_small, 4, cudaMemcpyDeviceToHost, st));
-  LM_CUDA(cudaStreamSynchronize(st));
-  R = reinterpret_cast<uint32_t*>(ws.h_small)[0];
 
-  // label values present in the input (np.unique(label_image), utils.py:294) only matter through max+1 sizing;
-  // the record table is sized 256.
-  rc = ws.reserve_regions(R);
-  if (rc) return rc;
-  LM_CUDA(cudaMemsetAsync(ws.r_area, 0, (size_t)(R + 1) * 4, st));
-  LM_CUDA(cudaMemsetAsync(ws.r_count, 0, (size_t)(R + 1) * 4, st));
-  LM_CUDA(cudaMemsetAsync(ws.r_value, 0, (size_t)(R + 1), st));
-  bbox_init_kernel<<<grid_for(R + 1, 256, num_sms), 256, 0, st>>>(ws.r_bbox, R);
-  region_stats_kernel<<<g, 256, 0, st>>>(d_labels, ws.parent, ws.rid, d, ws.r_area, ws.r_value, ws.r_bbox);
-  *launches += 2;
+  // Q2: region tables
+  const int gr = grid_for((size_t)cap + 1, 256, num_sms);
+  region_init_kernel<<<gr, 256, 0, st>>>(d_small, cap, ws.r_area, ws.r_count, ws.r_value, ws.r_bbox, ws.r_cur, ws.r_to_label,
+                                         ws.r_spare_id);
+  region_stats_kernel<<<g, 256, 0, st>>>(d_labels, ws.parent, ws.rid, d, cap, ws.r_area, ws.r_value, ws.r_bbox);
+  // Q3: ascending (area, id) order, per-label records, region -> label table
+  region_sort_kernel<<<1, 1024, 0, st>>>(d_small, cap, ws.r_area, reinterpret_cast<unsigned long long*>(ws.sort_keys), ws.r_order);
+  LM_CUDA(cudaMemsetAsync(ws.hash_keys, 0xFF, (size_t)ws.hash_cap * 8, st));
+  LM_CUDA(cudaMemsetAsync(ws.hash_min, 0xFF, (size_t)ws.hash_cap * 4, st));
+  record_insert_kernel<<<gr, 256, 0, st>>>(d_small, cap, ws.r_area, ws.r_value, reinterpret_cast<unsigned long long*>(ws.hash_keys),
+                                           ws.hash_min, ws.hash_cap - 1, ws.r_hslot);
+  record_lookup_kernel<<<gr, 256, 0, st>>>(d_small, cap, ws.r_value, ws.hash_min, ws.r_hslot, ws.r_to_label);
+  // Q4
+  MergeArgs ma;
+  ma.rid = ws.rid; ma.cur = ws.r_cur; ma.area = ws.r_area; ma.value = ws.r_value; ma.bbox = ws.r_bbox;
+  ma.record = d_record; ma.order = ws.r_order; ma.count = ws.r_count; ma.touched = ws.r_touched;
+  ma.spare_value = d_spare_value; ma.spare_id = ws.r_spare_id; ma.d_R = d_small + W_R; ma.cap = cap;
+  ma.skip_below = skip_below; ma.d = d;
+  merge_loop_kernel<<<1, 1024, 0, st>>>(ma);
+  // Q5
+  map_labels_kernel<<<g, 256, 0, st>>>(ws.rid, ws.r_cur, ws.r_to_label, d_spare_value, ws.mapped, n, d_present, cap);
+  *launches += 11;
 
-  // Q2/Q3 on the host: stable ascending-area order, per-label records, region -> label table
-  std::vector<uint32_t> h_area(R + 1), h_order(R);
-  std::vector<uint8_t> h_value(R + 1), h_to_label(R + 1, 0), h_spare_id(R + 1, 0);
-  uint32_t record[256];
-  uint8_t spare_value[256];
-  memset(record, 0, sizeof(record));
-  memset(spare_value, 0, sizeof(spare_value));
-  for (int i = 0; i < n_spare; ++i) {
-    if (spare[i] >= 0 && spare[i] < 256) spare_value[spare[i]] = 1;
-    if (spare[i] >= 0 && (uint32_t)spare[i] <= R) h_spare_id[spare[i]] = 1;  // the reference compares ids with values
-  }
-  if (R) {
-    LM_CUDA(cudaMemcpyAsync(h_area.data(), ws.r_area, (size_t)(R + 1) * 4, cudaMemcpyDeviceToHost, st));
-    LM_CUDA(cudaMemcpyAsync(h_value.data(), ws.r_value, (size_t)(R + 1), cudaMemcpyDeviceToHost, st));
-    LM_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t i = 0; i < R; ++i) h_order[i] = i + 1;
-    std::stable_sort(h_order.begin(), h_order.end(), [&](uint32_t x, uint32_t y) { return h_area[x] < h_area[y]; });
-    for (uint32_t k = 0; k < R; ++k) {  // utils.py:303-308
-      const uint32_t id = h_order[k];
-      const uint8_t v = h_value[id];
-      if (h_area[id] > record[v]) { record[v] = h_area[id]; h_to_label[id] = v; }
-    }
-    std::vector<uint32_t> h_cur(R + 1);
-    for (uint32_t i = 0; i <= R; ++i) h_cur[i] = i;
-    LM_CUDA(cudaMemcpyAsync(ws.r_cur, h_cur.data(), (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st));
-    LM_CUDA(cudaMemcpyAsync(ws.r_order, h_order.data(), (size_t)R * 4, cudaMemcpyHostToDevice, st));
-    LM_CUDA(cudaMemcpyAsync(ws.r_spare_id, h_spare_id.data(), (size_t)(R + 1), cudaMemcpyHostToDevice, st));
-    LM_CUDA(cudaMemcpyAsync(ws.r_to_label, h_to_label.data(), (size_t)(R + 1), cudaMemcpyHostToDevice, st));
-    // small tables: record at word 512.., spare_value bytes at byte offset 4096
-    uint32_t* d_record = d_small + 512;
-    uint8_t* d_spare_value = reinterpret_cast<uint8_t*>(ws.small) + 4096;
-    LM_CUDA(cudaMemcpyAsync(d_record, record, sizeof(record), cudaMemcpyHostToDevice, st));
-    LM_CUDA(cudaMemcpyAsync(d_spare_value, spare_value, 256, cudaMemcpyHostToDevice, st));
-    LM_CUDA(cudaStreamSynchronize(st));  // host vectors go out of scope later; keep it simple and safe
-
-    // Q4
-    MergeArgs ma;
-    ma.rid = ws.rid; ma.cur = ws.r_cur; ma.area = ws.r_area; ma.value = ws.r_value; ma.bbox = ws.r_bbox;
-    ma.record = d_record; ma.order = ws.r_order; ma.count = ws.r_count; ma.touched = ws.r_touched;
-    ma.spare_value = d_spare_value; ma.spare_id = ws.r_spare_id; ma.R = R; ma.skip_below = skip_below; ma.d = d;
-    merge_loop_kernel<<<1, 1024, 0, st>>>(ma);
-    *launches += 1;
-    // Q5
-    uint32_t* d_present = d_small + 8;
-    LM_CUDA(cudaMemsetAsync(d_present, 0, 256 * 4, st));
-    map_labels_kernel<<<g, 256, 0, st>>>(ws.rid, ws.r_cur, ws.r_to_label, d_spare_value, ws.mapped, n, d_present);
-    *launches += 1;
-  } else {
-    LM_CUDA(cudaMemsetAsync(ws.mapped, 0, n, st));
-    LM_CUDA(cudaMemsetAsync(d_small + 8, 0, 256 * 4, st));
-    uint32_t one = 1;
-    LM_CUDA(cudaMemcpyAsync(d_small + 8, &one, 4, cudaMemcpyHostToDevice, st));
-    LM_CUDA(cudaStreamSynchronize(st));
-  }
+  // R and the overflow flag travel to the pinned mirror now; the host looks at them in postprocess_finish
+  LM_CUDA(cudaMemcpyAsync(ws.h_small, d_small, 8, cudaMemcpyDeviceToHost, st));
 
   if (ws.debug_stage == 1) { LM_CUDA(cudaMemcpyAsync(d_out, ws.mapped, n, cudaMemcpyDeviceToDevice, st)); return 0; }
   if (ws.debug_stage == 2 || ws.debug_stage == 3) {
-    if (R) debug_ids_kernel<<<g, 256, 0, st>>>(ws.rid, ws.r_cur, d_out, n, ws.debug_stage == 3);
-    else LM_CUDA(cudaMemsetAsync(d_out, 0, n, st));
+    debug_ids_kernel<<<g, 256, 0, st>>>(ws.rid, ws.r_cur, d_out, n, ws.debug_stage == 3, cap);
     return (int)cudaGetLastError();
   }
   // Q6
   LM_CUDA(cudaMemsetAsync(d_out, 0, n, st));
-  rc = run_ccl<26>(ws.mapped, ws.parent, d, full, num_sms, st, launches, ws.ccl_reduced);
+  LM_CUDA(cudaMemsetAsync(ws.outside, 0, n, st));
+  rc = run_ccl<26>(ws.mapped, ws.parent, d, fullsrc, n, num_sms, st, launches, ws.ccl_rule);
   if (rc) return rc;
   LM_CUDA(cudaMemsetAsync(ws.area2, 0, n * 4, st));
-  unsigned long long* d_best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.small) + 8192);
-  LM_CUDA(cudaMemsetAsync(d_best, 0, 256 * 8, st));
   root_area_kernel<<<g, 256, 0, st>>>(ws.parent, ws.area2, n);
   best_root_kernel<<<g, 256, 0, st>>>(ws.mapped, ws.parent, ws.area2, d_best, n);
-  *launches += 2;
-  uint32_t h_present[256];
-  unsigned long long h_best[256];
-  LM_CUDA(cudaMemcpyAsync(h_present, d_small + 8, sizeof(h_present), cudaMemcpyDeviceToHost, st));
-  LM_CUDA(cudaMemcpyAsync(h_best, d_best, sizeof(h_best), cudaMemcpyDeviceToHost, st));
-  LM_CUDA(cudaStreamSynchronize(st));
-  bool first_skipped = false;
-  int* d_bbox1 = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws.small) + 16384);
-  LM_CUDA(cudaMemsetAsync(ws.outside, 0, n, st));
+  first_present_kernel<<<1, 32, 0, st>>>(d_small);
+  *launches += 3;
+
+  // the labels to finalise: 1..max_label when the caller knows a bound (no host round trip; absent labels cost a few
+  // empty launches), otherwise the values that occur (ONE synchronisation)
+  bool todo[256];
+  memset(todo, 0, sizeof(todo));
+  if (max_label >= 0) {
+    for (int v = 1; v <= max_label && v < 256; ++v) todo[v] = true;  // 0, when present, is always np.unique(...)[0]
+  } else {
+    uint32_t* h_present = reinterpret_cast<uint32_t*>(ws.h_small) + 16;
+    LM_CUDA(cudaMemcpyAsync(h_present, d_present, 256 * 4, cudaMemcpyDeviceToHost, st));
+    LM_CUDA(cudaStreamSynchronize(st));
+    for (int v = 0; v < 256; ++v) todo[v] = h_present[v] != 0;
+  }
+  BoxSrc boxsrc;
+  boxsrc.fixed = full; boxsrc.dyn = d_bbox1; boxsrc.gate = d_gate;
+  BoxSrc gated_full = fullsrc;
+  gated_full.gate = d_gate;
   for (int v = 0; v < 256; ++v) {
-    if (!h_present[v]) continue;
-    if (!first_skipped) { first_skipped = true; continue; }  // np.unique(outmask_mapped)[1:], utils.py:355
-    const uint32_t root = (uint32_t)(h_best[v] & 0xFFFFFFFFull);
-    int hb[6] = {1 << 30, -1, 1 << 30, -1, 1 << 30, -1};
-    LM_CUDA(cudaMemcpyAsync(d_bbox1, hb, sizeof(hb), cudaMemcpyHostToDevice, st));
-    keep_complement_kernel<<<g, 256, 0, st>>>(ws.mapped, ws.parent, (uint8_t)v, root, ws.tmp, d, d_bbox1);
-    *launches += 1;
+    if (!todo[v]) continue;
+    label_begin_kernel<<<1, 32, 0, st>>>(d_small, v);   // gate: present and not np.unique(...)[0] (utils.py:355)
+    keep_complement_kernel<<<g, 256, 0, st>>>(ws.mapped, ws.parent, (uint8_t)v, d_best, ws.tmp, d, d_bbox1, d_gate);
+    *launches += 2;
     if (S == 1) {
-      rc = run_ccl<4>(ws.tmp, ws.parent2, d, full, num_sms, st, launches);
+      rc = run_ccl<4>(ws.tmp, ws.parent2, d, gated_full, n, num_sms, st, launches);
       if (rc) return rc;
-      LM_CUDA(cudaMemsetAsync(ws.area2, 0, n * 4, st));
-      root_area_kernel<<<g, 256, 0, st>>>(ws.parent2, ws.area2, n);
-      paint_area_closing_kernel<<<g, 256, 0, st>>>(ws.parent2, ws.area2, (uint8_t)v, d_out, n, 64u);
-      *launches += 2;
-      // area2 is reused by the next label: it is re-zeroed above; restore root areas is not needed any more
+      gated_zero_kernel<<<g, 256, 0, st>>>(ws.area2, n, d_gate);
+      gated_root_area_kernel<<<g, 256, 0, st>>>(ws.parent2, ws.area2, n, d_gate);
+      paint_area_closing_kernel<<<g, 256, 0, st>>>(ws.parent2, ws.area2, (uint8_t)v, d_out, n, 64u, d_gate);
+      *launches += 3;
     } else {
-      LM_CUDA(cudaMemcpyAsync(hb, d_bbox1, sizeof(hb), cudaMemcpyDeviceToHost, st));
-      LM_CUDA(cudaStreamSynchronize(st));
-      Box b;
-      b.z0 = std::max(hb[0] - 1, 0); b.z1 = std::min(hb[1] + 1, S);
-      b.y0 = std::max(hb[2] - 1, 0); b.y1 = std::min(hb[3] + 1, H);
-      b.x0 = std::max(hb[4] - 1, 0); b.x1 = std::min(hb[5] + 1, W);
-      rc = run_ccl<6>(ws.tmp, ws.parent2, d, b, num_sms, st, launches);
+      rc = run_ccl<6>(ws.tmp, ws.parent2, d, boxsrc, n, num_sms, st, launches);
       if (rc) return rc;
-      const size_t bn = (size_t)(b.z1 - b.z0) * (b.y1 - b.y0) * (b.x1 - b.x0);
-      const int gb = grid_for(bn, 256, num_sms);
-      seed_outside_kernel<<<gb, 256, 0, st>>>(ws.parent2, ws.outside, d, b);
-      paint_filled_kernel<<<gb, 256, 0, st>>>(ws.parent2, ws.outside, (uint8_t)v, d_out, d, b);
-      clear_outside_kernel<<<gb, 256, 0, st>>>(ws.parent2, ws.outside, d, b);
+      seed_outside_kernel<<<g, 256, 0, st>>>(ws.parent2, ws.outside, d, boxsrc);
+      paint_filled_kernel<<<g, 256, 0, st>>>(ws.parent2, ws.outside, (uint8_t)v, d_out, d, boxsrc);
+      clear_outside_kernel<<<g, 256, 0, st>>>(ws.outside, d, boxsrc);
       *launches += 3;
     }
   }
   return (int)cudaGetLastError();
+}
+
+int postprocess_finish(PostScratch& ws) {
+  if (!ws.h_small) return 0;
+  uint32_t* h = reinterpret_cast<uint32_t*>(ws.h_small);
+  ws.clear_sticky = true;   // the next run starts a new observation window
+  ws.last_regions = h[W_MAXR];
+  if (h[W_OVERFLOW]) {
+    ws.want_regions = h[W_MAXR] + h[W_MAXR] / 8 + 1024;
+    h[W_OVERFLOW] = 0;
+    return 1;
+  }
+  return 0;
 }
 
 __global__ void select_root_kernel(const uint32_t* __restrict__ parent, uint32_t root, uint8_t* __restrict__ out, size_t n) {
@@ -727,18 +969,18 @@ int keep_largest_component_device(PostScratch& ws, const uint8_t* d_mask, int S,
   const int g = grid_for(n, 256, num_sms);
   int64_t launches = 0;
   binarize_kernel<<<g, 256, 0, st>>>(d_mask, ws.tmp, n);
-  rc = run_ccl<26>(ws.tmp, ws.parent, d, full, num_sms, st, &launches, ws.ccl_reduced);
+  rc = run_ccl<26>(ws.tmp, ws.parent, d, fixed_box(full), n, num_sms, st, &launches, ws.ccl_rule);
   if (rc) return rc;
   LM_CUDA(cudaMemsetAsync(ws.area2, 0, n * 4, st));
-  unsigned long long* d_best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.small) + 8192);
+  unsigned long long* d_best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws.small) + B_BEST);
   LM_CUDA(cudaMemsetAsync(d_best, 0, 256 * 8, st));
   root_area_kernel<<<g, 256, 0, st>>>(ws.parent, ws.area2, n);
   best_root_kernel<<<g, 256, 0, st>>>(ws.tmp, ws.parent, ws.area2, d_best, n);
-  unsigned long long h_best = 0;
-  LM_CUDA(cudaMemcpyAsync(&h_best, d_best + 1, 8, cudaMemcpyDeviceToHost, st));
-  LM_CUDA(cudaStreamSynchronize(st));
-  if (h_best == 0ull) { LM_CUDA(cudaMemsetAsync(d_out, 0, n, st)); return -21; }  // empty mask: the reference raises (argsort of [])
-  select_root_kernel<<<g, 256, 0, st>>>(ws.parent, (uint32_t)(h_best & 0xFFFFFFFFull), d_out, n);
+  unsigned long long* h_best = reinterpret_cast<unsigned long long*>(ws.h_small) + 1024;
+  LM_CUDA(cudaMemcpyAsync(h_best, d_best + 1, 8, cudaMemcpyDeviceToHost, st));
+  LM_CUDA(cudaStreamSynchronize(st));  // the reference raises on an empty mask: the host must know
+  if (*h_best == 0ull) { LM_CUDA(cudaMemsetAsync(d_out, 0, n, st)); return -21; }  // empty mask: argsort of []
+  select_root_kernel<<<g, 256, 0, st>>>(ws.parent, (uint32_t)(*h_best & 0xFFFFFFFFull), d_out, n);
   return (int)cudaGetLastError();
 }
 
@@ -749,16 +991,12 @@ int reshape_device(const uint8_t* d_masks, const int32_t* d_boxes, int S, int H,
   return (int)cudaGetLastError();
 }
 
-int fuse_device(uint8_t* d_res_l, const uint8_t* d_res_r, size_t n, uint32_t* d_scratch, int* spare_out, int num_sms,
+int fuse_device(uint8_t* d_res_l, const uint8_t* d_res_r, size_t n, uint32_t* d_scratch, int32_t* d_spare_out, int num_sms,
                 cudaStream_t st) {
   LM_CUDA(cudaMemsetAsync(d_scratch, 0, 4, st));
   max_u8_kernel<<<grid_for(n, 256, num_sms), 256, 0, st>>>(d_res_l, n, d_scratch);
-  uint32_t mx = 0;
-  LM_CUDA(cudaMemcpyAsync(&mx, d_scratch, 4, cudaMemcpyDeviceToHost, st));
-  LM_CUDA(cudaStreamSynchronize(st));
-  const int spare = (int)((mx + 1) & 0xFF);  // uint8 arithmetic: res_l.max() + 1 (mask.py:228)
-  fuse_kernel<<<grid_for(n, 256, num_sms), 256, 0, st>>>(d_res_l, d_res_r, n, (uint8_t)spare);
-  *spare_out = spare;
+  spare_from_max_kernel<<<1, 32, 0, st>>>(d_scratch, d_spare_out);
+  fuse_kernel<<<grid_for(n, 256, num_sms), 256, 0, st>>>(d_res_l, d_res_r, n, d_spare_out);
   return (int)cudaGetLastError();
 }
 

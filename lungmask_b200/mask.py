@@ -169,7 +169,7 @@ class LMInferer:
         logger.info(f"Apply: {self.modelname}")
         logger.info(f"Apply: {self.fillmodel}")
         logger.info("Fusing results... this may take up to several minutes!")
-        return self.engine.apply_fused(0, 1, vol)
+        return self.engine.apply_fused(0, 1, vol, postprocess=self.volume_postprocessing)
 
     def apply(self, image) -> np.ndarray:
         """Segments a volume: numpy (slices, H, W) or sitk.Image -> uint8 labels of the same shape

@@ -9,6 +9,9 @@ Fixtures (small, committed):
   forward.npz        resunet.UNet (get_model configuration) scores on one phantom slice, sub-sampled,
                      for seeded synthetic state_dicts (K = 3 and 6)
   e2e.json           LMInferer(force_cpu=True).apply label histograms for seeded weights / volumes
+  fusion.npz         LMInferer(modelname K=6, fillmodel K=3, force_cpu=True): the two inner _inference results
+                     (res_l, res_r) and apply() for volume_postprocessing True / False (mask.py:223-232), plus
+                     the single-model apply() volumes behind e2e.json's histograms
 """
 import json
 import os
@@ -57,7 +60,7 @@ def main():
         post[f"out{i}_skip1"] = ref.utils.postprocessing(lab, skip_below=1, disable_tqdm=True)
     np.savez_compressed(os.path.join(GOLD, "postprocess.npz"), **post)
 
-    fwd, e2e = {}, []
+    fwd, e2e, fus, paths = {}, [], {}, {}
     for K in (3, 6):
         sd = synth.random_state_dict(K, seed=10 + K)
         model = ref.resunet.UNet(n_classes=K, padding=True, depth=5, up_mode="upsample", batch_norm=True, residual=False)
@@ -71,11 +74,23 @@ def main():
         fwd[f"scores_K{K}"] = y[:, :, 3::8, 5::8].copy()
         p = os.path.join(tempfile.gettempdir(), f"golden_K{K}.pth")
         torch.save(sd, p)
+        paths[K] = p
         inf = ref.mask.LMInferer(modelname="R231", modelpath=p, force_cpu=True, batch_size=2, tqdm_disable=True)
         v2 = synth.phantom(4, 200, 216, seed=30 + K)
         out = inf.apply(v2)
+        fus[f"apply_K{K}"] = out
         e2e.append({"K": K, "weights_seed": 10 + K, "volume": [4, 200, 216], "volume_seed": 30 + K,
                     "histogram": np.bincount(out.ravel(), minlength=K).tolist()})
+    # fusion (mask.py:223-232): base = the K=6 weights, fill = the K=3 weights, on the K=6 e2e volume
+    vf = synth.phantom(4, 200, 216, seed=36)
+    for vp in (True, False):
+        inf = ref.mask.LMInferer(modelname="LTRCLobes", modelpath=paths[6], fillmodel="R231", fillmodel_path=paths[3],
+                                 force_cpu=True, batch_size=2, volume_postprocessing=vp, tqdm_disable=True)
+        tag = "pp" if vp else "nopp"
+        fus[f"res_l_{tag}"] = inf._inference(vf, inf.model)
+        fus[f"res_r_{tag}"] = inf._inference(vf, inf.fillmodelm)
+        fus[f"fused_{tag}"] = inf.apply(vf)
+    np.savez_compressed(os.path.join(GOLD, "fusion.npz"), **fus)
     np.savez_compressed(os.path.join(GOLD, "forward.npz"), **fwd)
     json.dump(e2e, open(os.path.join(GOLD, "e2e.json"), "w"), indent=1)
     print("golden fixtures written to", GOLD)

@@ -337,14 +337,21 @@ def inference(volume: np.ndarray, sd: dict, batch_size: int = 20, volume_postpro
     return out.astype(np.uint8)
 
 
-def fuse(res_l: np.ndarray, res_r: np.ndarray) -> np.ndarray:
-    """mask.py:228-232: voxels the fill model marks as lung but the base model left empty get a
-    spare label that postprocessing then dissolves into neighbouring lobes."""
+def fuse_pre(res_l: np.ndarray, res_r: np.ndarray):
+    """mask.py:228-230: the array (and spare value) that utils.postprocessing receives at mask.py:232.  Voxels the fill
+    model marks as lung but the base model left empty get a spare label; voxels the fill model calls background are
+    cleared.  `res_l.max() + 1` is uint8 arithmetic, as in the reference."""
     res_l = res_l.copy()
     spare_value = res_l.max() + 1
     res_l[np.logical_and(res_l == 0, res_r > 0)] = spare_value
     res_l[res_r == 0] = 0
-    return postprocessing(res_l, spare=[spare_value])
+    return res_l, spare_value
+
+
+def fuse(res_l: np.ndarray, res_r: np.ndarray) -> np.ndarray:
+    """mask.py:228-232: fuse_pre, then postprocessing dissolves the spare label into neighbouring lobes."""
+    pre, spare_value = fuse_pre(res_l, res_r)
+    return postprocessing(pre, spare=[spare_value])
 
 
 def apply(volume: np.ndarray, sd: dict, fill_sd: dict = None, batch_size: int = 20,

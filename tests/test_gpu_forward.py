@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import restate, synth
+from _parity import explain_fused, explain_inference, fmt
 
 pytestmark = pytest.mark.gpu
 
@@ -51,51 +52,63 @@ def test_forward_batch_invariance(engine, models):
     assert np.array_equal(a, b)
 
 
-def _dice(a, b):
-    out = []
-    for v in np.union1d(np.unique(a), np.unique(b)):
-        if v == 0:
-            continue
-        x, y = a == v, b == v
-        out.append(2.0 * (x & y).sum() / max(1, x.sum() + y.sum()))
-    return min(out) if out else 1.0
-
-
 def test_apply_volume_end_to_end(engine, models):
+    """lm_apply_volume against restate.inference with the every-voxel-explained protocol of tests/_parity.py
+    (north_star: labels bit-exact, scores within 1e-4)."""
     sd = models[3]
     m = _blob(sd)
     engine.load_weights(0, m.blob, m.n_classes)
     vol = synth.phantom(6, 300, 414, seed=8)
-    taps = {}
-    want = restate.inference(vol, sd, batch_size=3, taps=taps)
-    got = engine.apply_volume(0, vol)
-    flips = int((got != want).sum())
-    print("end-to-end voxels differing: %d of %d, dice(min over labels) %.6f" % (flips, want.size, _dice(got, want)))
-    # stage isolation: feeding the oracle's argmax volume through the device post-processing is bit-exact
-    post = engine.postprocess(taps["labels"])
-    assert np.array_equal(post, taps["post"])
-    assert _dice(got, want) > 0.999
+    rep = explain_inference(engine, 0, vol, sd, batch=3)
+    print("end to end: " + fmt(rep))
     t = engine.last_timings()
     assert t["kernel_launches"] > 30
-    # no post-processing flag
-    got_np = engine.apply_volume(0, vol, postprocess=False)
-    want_np = restate.inference(vol, sd, batch_size=3, volume_postprocessing=False)
-    assert _dice(got_np, want_np) > 0.999
+    rep = explain_inference(engine, 0, vol, sd, batch=3, postprocess=False)   # LMInferer(volume_postprocessing=False)
+    print("end to end, no post-processing: " + fmt(rep))
 
 
-def test_apply_fused(engine, models):
+@pytest.mark.parametrize("postprocess", [True, False])
+def test_apply_fused(engine, models, postprocess):
+    """LMInferer.apply with a fill model (mask.py:223-232): both inner inferences explained, the fusion glue
+    (lm_fuse) and the original-resolution post-processing bit-exact in isolation, the fused volume explained by the
+    inner results.  volume_postprocessing=False reaches the inner inferences only (mask.py:191-194)."""
     m6, m3 = _blob(models[6]), _blob(models[3])
     engine.load_weights(0, m6.blob, m6.n_classes)
     engine.load_weights(1, m3.blob, m3.n_classes)
     vol = synth.phantom(4, 200, 216, seed=9)
-    want = restate.apply(vol, models[6], fill_sd=models[3], batch_size=2)
-    got = engine.apply_fused(0, 1, vol)
-    print("fused voxels differing: %d of %d" % (int((got != want).sum()), want.size))
-    # stage isolation of the fusion glue + original-resolution post-processing
-    res_l = restate.inference(vol, models[6], batch_size=2)
-    res_r = restate.inference(vol, models[3], batch_size=2)
-    assert np.array_equal(restate.fuse(res_l, res_r), restate.fuse(res_l, res_r))
-    assert _dice(got, want) > 0.99
+    rep = explain_fused(engine, 0, 1, vol, models[6], models[3], batch=2, postprocess=postprocess)
+    print("fused (volume_postprocessing=%s): %s" % (postprocess, fmt(rep)))
+
+
+def test_fuse_kernel_edge_cases(engine):
+    """lm_fuse alone (mask.py:228-230) on crafted inputs: the spare value is uint8 arithmetic (255 + 1 wraps to 0)."""
+    rng = np.random.default_rng(11)
+    for top in (5, 254, 255):
+        res_l = rng.integers(0, 3, size=(3, 40, 56)).astype(np.uint8)
+        res_l[res_l == 2] = top
+        res_r = rng.integers(0, 3, size=res_l.shape).astype(np.uint8)
+        want, spare = restate.fuse_pre(res_l, res_r)
+        got, gspare = engine.fuse(res_l, res_r)
+        assert gspare == int(spare) and np.array_equal(got, want), top
+
+
+def test_lminferer_fused_honours_volume_postprocessing(tmp_path, models):
+    """LMInferer(fillmodel=..., volume_postprocessing=False) must differ from the default exactly as the
+    reference does (inner post-processing skipped, fusion post-processing kept)."""
+    import torch
+    from lungmask_b200 import LMInferer
+    p6, p3 = str(tmp_path / "l.pth"), str(tmp_path / "r.pth")
+    torch.save(models[6], p6)
+    torch.save(models[3], p3)
+    vol = synth.phantom(4, 200, 216, seed=9)
+    outs = {}
+    for vp in (True, False):
+        inf = LMInferer(modelname="LTRCLobes", modelpath=p6, fillmodel="R231", fillmodel_path=p3, batch_size=4,
+                        volume_postprocessing=vp, tqdm_disable=True)
+        outs[vp] = inf.apply(vol)
+        assert np.array_equal(outs[vp], inf.engine.apply_fused(0, 1, vol, postprocess=vp))
+        inf.engine.close()
+    assert not np.array_equal(outs[True], outs[False])
 
 
 def test_lminferer_surface(tmp_path, models):

@@ -1,10 +1,13 @@
 """BASELINE.json's full-size configurations through size-independent properties (the CPU oracle would need
 minutes to hours at these sizes): slice independence of the per-slice stages, run-to-run determinism,
 label range, and the fusion rule's invariants."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import synth
+from _parity import explain_fused, explain_inference, fmt
 
 pytestmark = pytest.mark.gpu
 
@@ -85,3 +88,48 @@ def test_c2_r231_300_slices_through_lminferer(tmp_path):
     assert np.array_equal(out, inf.apply(vol))
     t = inf.engine.last_timings()
     assert t["kernel_launches"] > 9 * 26
+
+
+# ---- the benchmarked configurations against the CPU oracle, with the bench's own weights ------------------------------
+# (the oracle's fp32 forward runs at about 3 slices/s on the GPU box's host cores: C2 is compared in full, C3 / C4 on a
+#  contiguous 64-slice sub-volume, sizes chosen with LM_FULLSIZE_SLICES / LM_SUBSAMPLE_SLICES)
+def _bench_weights(K, seed):
+    import bench
+    return bench.get_weights(K, seed=seed)
+
+
+def _load_sd(eng, slot, sd):
+    from lungmask_b200.mask import NativeModel
+    m = NativeModel(sd)
+    eng.load_weights(slot, m.blob, m.n_classes)
+
+
+def test_c2_bench_workload_against_oracle(big_engine):
+    """C2 exactly as bench.py runs it (same phantom, same trained-looking weights), end to end against restate.inference:
+    scores within 1e-4, every argmax flip on a sub-tolerance margin, integer stages bit-exact, every differing output
+    voxel explained (tests/_parity.py)."""
+    import bench
+    S = int(os.environ.get("LM_FULLSIZE_SLICES", bench.S_VOL))
+    sd = _bench_weights(3, 7)
+    _load_sd(big_engine, 0, sd)
+    vol = synth.phantom(bench.S_VOL, seed=100)[:S]
+    rep = explain_inference(big_engine, 0, vol, sd, batch=20)
+    print("C2 (%d slices, bench weights): %s" % (S, fmt(rep)))
+    assert rep["dice"] >= 0.9999 or rep["label_flips"] > 0
+
+
+def test_c3_c4_subvolume_against_oracle(big_engine):
+    """C3 (6-class, batch 32) and C4 (fusion) with trained-looking weights on a contiguous sub-volume of the 512- /
+    300-slice phantoms."""
+    n = int(os.environ.get("LM_SUBSAMPLE_SLICES", "64"))
+    sd6, sd3 = _bench_weights(6, 8), _bench_weights(3, 7)
+    _load_sd(big_engine, 0, sd6)
+    _load_sd(big_engine, 1, sd3)
+    v3 = synth.phantom(512, seed=101)[256 - n // 2:256 + n // 2]
+    rep = explain_inference(big_engine, 0, v3, sd6, batch=32)
+    print("C3 (%d-slice sub-volume): %s" % (n, fmt(rep)))
+    v4 = synth.phantom(300, seed=102)[150 - n // 2:150 + n // 2]
+    rep = explain_fused(big_engine, 0, 1, v4, sd6, sd3, batch=20)
+    print("C4 fusion (%d-slice sub-volume): %s" % (n, fmt(rep)))
+    rep = explain_fused(big_engine, 0, 1, v4[:8], sd6, sd3, batch=20, postprocess=False)
+    print("C4 fusion, volume_postprocessing=False (8 slices): %s" % fmt(rep))

@@ -101,3 +101,47 @@ def test_keep_largest_component_bit_exact(engine):
     two[0, 1, 1:4] = 1
     two[0, 6, 2:5] = 1
     assert np.array_equal(restate.keep_largest_connected_component(two != 0), engine.keep_largest_component(two).astype(bool))
+
+
+def test_ccl_rules_agree(engine):
+    """The pruned neighbour rule of the 26-connected labelling (default) against probing all 13 backward neighbours
+    (lm_set_option("ccl_rule", 0)): identical post-processing on clean, speckled and pure-noise label volumes (the CPU
+    emulation of both kernels against scipy is tests/test_ccl_neighbour_rule.py)."""
+    rng = np.random.default_rng(7)
+    vols = [synth.label_noise_volume(12, 3, seed=5, speckle=0.0), synth.label_noise_volume(12, 6, seed=15, speckle=2e-3),
+            synth.label_noise_volume(7, 3, seed=25, speckle=2e-2, H=130, W=97),   # rows that are not a multiple of 32 voxels
+            rng.integers(0, 4, size=(5, 33, 47)).astype(np.uint8)]
+    for lab in vols:
+        want = engine.postprocess(lab)
+        engine.set_option("ccl_rule", 0)
+        try:
+            got = engine.postprocess(lab)
+        finally:
+            engine.set_option("ccl_rule", 1)
+        assert np.array_equal(got, want)
+        assert np.array_equal(want, restate.postprocessing(lab))
+
+
+def test_region_table_overflow_is_rerun(engine):
+    """The region count stays on the device; when it exceeds the table capacity the device raises a flag and the call
+    is repeated with larger tables (lm_set_option("post_region_capacity", n) shrinks them for this test)."""
+    rng = np.random.default_rng(9)
+    noise = rng.integers(0, 4, size=(4, 40, 40)).astype(np.uint8)   # thousands of regions
+    want = restate.postprocessing(noise)
+    assert np.array_equal(engine.postprocess(noise), want)
+    engine.set_option("post_region_capacity", 64)
+    try:
+        assert np.array_equal(engine.postprocess(noise), want)          # overflows, grows, runs again
+        assert np.array_equal(engine.postprocess(noise, spare=[3]), restate.postprocessing(noise, spare=[3]))
+    finally:
+        engine.set_option("post_region_capacity", 1 << 16)
+
+
+def test_sort_paths(engine):
+    """region_sort_kernel: the shared-memory path (<= 4096 regions) and the global-memory path give the reference's
+    stable ascending-area order (checked through the bit-exact post-processing of volumes on either side)."""
+    rng = np.random.default_rng(13)
+    small = rng.integers(0, 3, size=(2, 30, 30)).astype(np.uint8)       # a few hundred regions
+    big = rng.integers(0, 5, size=(6, 64, 64)).astype(np.uint8)         # > 4096 regions
+    for lab in (small, big):
+        assert np.array_equal(engine.postprocess(lab), restate.postprocessing(lab))

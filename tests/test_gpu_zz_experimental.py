@@ -39,16 +39,3 @@ def test_experimental_kernel_is_bit_identical(engine, setup, option):
     l2, s2 = _forward(engine, resized, **{option: 1})
     assert np.array_equal(labels, l2)
     assert np.array_equal(scores, s2)
-
-
-def test_reduced_ccl_neighbour_set_is_bit_identical(engine):
-    """postprocess with lm_set_option("ccl_reduced", 1) == default post-processing on speckled label volumes."""
-    for seed, speckle in ((5, 0.0), (15, 2e-3), (25, 2e-2)):
-        lab = synth.label_noise_volume(12, 3, seed=seed, speckle=speckle)
-        want = engine.postprocess(lab)
-        engine.set_option("ccl_reduced", 1)
-        try:
-            got = engine.postprocess(lab)
-        finally:
-            engine.set_option("ccl_reduced", 0)
-        assert np.array_equal(got, want)
