@@ -74,11 +74,40 @@ LM_API int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int
  * mask.py:232 is unconditional, exactly as in the reference. */
 LM_API int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, int flags,
                           uint8_t* out);
+/* Same with a device-resident input volume and output (no host<->device copies). */
+LM_API int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const int16_t* d_vol, int S, int H, int W, int flags,
+                              uint8_t* d_out);
 /* The fusion glue alone, mask.py:228-230: spare = res_l.max() + 1 (uint8 arithmetic); res_l[(res_l == 0) & (res_r > 0)]
  * = spare; res_l[res_r == 0] = 0.  Host (S,H,W) uint8 in, fused (S,H,W) uint8 + the spare value out (parity tap: the
  * array utils.postprocessing(res_l, spare=[spare]) receives at mask.py:232). */
 LM_API int lm_fuse(lm_engine* e, const uint8_t* res_l, const uint8_t* res_r, int S, int H, int W, uint8_t* fused,
                    int* spare_value);
+
+/* ---- one volume over several GPUs (the reference is single-device, mask.py:118-121) ----------------
+ * One process and one engine per GPU.  Slices are independent up to the 3-D post-processing (utils.py:48-51,
+ * mask.py:173-187,196-202 vs utils.py:293-358): rank r of `world` runs pre-processing and the network on the contiguous
+ * slice range [r * ceil(S/world), (r+1) * ceil(S/world)) and the uint8 argmax volume (plus the crop boxes) is
+ * all-gathered once - by the engine itself: every rank owns a gather block in device memory that its peers map through
+ * CUDA IPC, a rank pushes its slab into every peer's block over NVLink and raises an epoch flag there; post-processing
+ * and reshape then run replicated on the gathered volume and every rank holds the whole result.
+ *   lm_shard_init     allocates this rank's gather block for volumes of up to max_slices slices
+ *   lm_shard_export   writes the block's IPC handle (lm_shard_handle_bytes() bytes) - exchange it by any host channel
+ *   lm_shard_connect  maps the peers' blocks; `handles` = world handles in rank order (this rank's own is ignored)
+ *   lm_apply_volume_sharded      every rank passes the SAME (S,H,W) host volume (only its slab is copied to the device)
+ *                                and receives the whole (S,H,W) result (out may be NULL on ranks that do not need it)
+ *   lm_apply_volume_sharded_dev  device-resident whole-volume buffers on this rank's device (only the slab is read)
+ *   lm_shard_labels   parity / alternative-collective tap: device pointers of this rank's gathered boxes (int32 x 4
+ *                     per slice) and labels (256*256 bytes per slice), and the slice capacity
+ * The calls are collective: every rank must make them in the same order (a bounded device-side wait turns a missing
+ * peer into error -50 instead of a hang).  world == 1 needs no export / connect. */
+LM_API int lm_shard_init(lm_engine* e, int rank, int world, int max_slices);
+LM_API size_t lm_shard_handle_bytes(void);
+LM_API int lm_shard_export(lm_engine* e, void* handle_out);
+LM_API int lm_shard_connect(lm_engine* e, const void* handles);
+LM_API int lm_shard_labels(lm_engine* e, void** d_boxes, void** d_labels, size_t* slice_cap);
+LM_API int lm_apply_volume_sharded(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out);
+LM_API int lm_apply_volume_sharded_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags,
+                                       uint8_t* d_out);
 
 /* ---- stage-level entry points (each mirrors one reference function; used by the parity tests) ---- */
 

@@ -39,6 +39,14 @@ def lib():
         "lm_apply_volume": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_volume_dev": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_fused": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
+        "lm_apply_fused_dev": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
+        "lm_shard_init": ([vp, i32, i32, i32], i32),
+        "lm_shard_handle_bytes": ([], C.c_size_t),
+        "lm_shard_export": ([vp, vp], i32),
+        "lm_shard_connect": ([vp, vp], i32),
+        "lm_shard_labels": ([vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_size_t)], i32),
+        "lm_apply_volume_sharded": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
+        "lm_apply_volume_sharded_dev": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_fuse": ([vp, u8p, u8p, i32, i32, i32, u8p, C.POINTER(i32)], i32),
         "lm_preprocess": ([vp, i16p, i32, i32, i32, i32, i32, i32, i16p, i32p], i32),
         "lm_simple_bodymask": ([vp, i16p, i32, i32, u8p], i32),
@@ -61,7 +69,9 @@ def lib():
 
 
 EXPORTS = ["lm_create", "lm_destroy", "lm_last_error", "lm_device", "lm_batch_capacity", "lm_weight_blob_floats",
-           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_fuse", "lm_preprocess",
+           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_apply_fused_dev", "lm_fuse", "lm_preprocess",
+           "lm_shard_init", "lm_shard_handle_bytes", "lm_shard_export", "lm_shard_connect", "lm_shard_labels",
+           "lm_apply_volume_sharded", "lm_apply_volume_sharded_dev",
            "lm_simple_bodymask", "lm_forward", "lm_forward_dev", "lm_postprocess", "lm_reshape_masks",
            "lm_keep_largest_component",
            "lm_last_timings", "lm_set_option", "lm_last_conv_timing",
@@ -78,6 +88,20 @@ def _check(rc):
 
 
 def _as(a, dtype, ndim=None):
+    """C-contiguous array of `dtype` for the C ABI.  Only value-preserving conversions happen here: a float volume is
+    never truncated and an int32 / uint16 volume never wraps silently (integers of another width are range-checked);
+    LMInferer / utils do the reference-compatible dtype handling before they get here."""
+    a = np.asarray(a)
+    dtype = np.dtype(dtype)
+    if a.dtype != dtype:
+        if a.dtype == bool or np.can_cast(a.dtype, dtype, casting="safe"):
+            pass
+        elif np.issubdtype(a.dtype, np.integer) and np.issubdtype(dtype, np.integer):
+            info = np.iinfo(dtype)
+            if a.size and (a.min() < info.min or a.max() > info.max):
+                raise TypeError("values of the %s array do not fit %s" % (a.dtype, dtype))
+        else:
+            raise TypeError("refusing to convert %s to %s (lossy); convert explicitly" % (a.dtype, dtype))
     a = np.ascontiguousarray(a, dtype=dtype)
     if ndim is not None and a.ndim != ndim:
         raise ValueError("expected %d-d array, got shape %s" % (ndim, a.shape))
@@ -134,6 +158,48 @@ class Engine:
         _check(lib().lm_apply_fused(self._h, slot_base, slot_fill, _ptr(vol), S, H, W,
                                     0 if postprocess else FLAG_NO_POSTPROCESS, _ptr(out)))
         return out
+
+    def apply_fused_dev(self, slot_base, slot_fill, d_vol_ptr, shape, d_out_ptr, postprocess=True):
+        S, H, W = shape
+        _check(lib().lm_apply_fused_dev(self._h, slot_base, slot_fill, C.c_void_p(d_vol_ptr), S, H, W,
+                                        0 if postprocess else FLAG_NO_POSTPROCESS, C.c_void_p(d_out_ptr)))
+
+    # ---- one volume over several GPUs (one engine per rank; see include/lungmask_b200.h)
+    def shard_init(self, rank, world, max_slices):
+        _check(lib().lm_shard_init(self._h, int(rank), int(world), int(max_slices)))
+        self.shard_rank, self.shard_world = int(rank), int(world)
+
+    def shard_export(self):
+        buf = C.create_string_buffer(int(lib().lm_shard_handle_bytes()))
+        _check(lib().lm_shard_export(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def shard_connect(self, handles):
+        """`handles`: the ranks' shard_export() results in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != self.shard_world * int(lib().lm_shard_handle_bytes()):
+            raise ValueError("shard_connect expects %d handles" % self.shard_world)
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(lib().lm_shard_connect(self._h, C.cast(buf, C.c_void_p)))
+
+    def shard_labels(self):
+        """(device pointer of the gathered boxes, device pointer of the gathered labels, slice capacity)"""
+        b, l, cap = C.c_void_p(), C.c_void_p(), C.c_size_t(0)
+        _check(lib().lm_shard_labels(self._h, C.byref(b), C.byref(l), C.byref(cap)))
+        return b.value, l.value, int(cap.value)
+
+    def apply_volume_sharded(self, slot, vol, postprocess=True, want_output=True):
+        vol = _as(vol, np.int16, 3)
+        S, H, W = vol.shape
+        out = np.empty(vol.shape, np.uint8) if want_output else None
+        _check(lib().lm_apply_volume_sharded(self._h, slot, _ptr(vol), S, H, W, 0 if postprocess else FLAG_NO_POSTPROCESS,
+                                             _ptr(out) if out is not None else None))
+        return out
+
+    def apply_volume_sharded_dev(self, slot, d_vol_ptr, shape, d_out_ptr, postprocess=True):
+        S, H, W = shape
+        _check(lib().lm_apply_volume_sharded_dev(self._h, slot, C.c_void_p(d_vol_ptr), S, H, W,
+                                                 0 if postprocess else FLAG_NO_POSTPROCESS, C.c_void_p(d_out_ptr)))
 
     def fuse(self, res_l, res_r):
         """mask.py:228-230 -> (fused uint8 volume before the post-processing, spare value)."""

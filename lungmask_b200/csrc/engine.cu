@@ -15,6 +15,7 @@
 #include "forward_misc.cuh"
 #include "postproc.cuh"
 #include "preproc.cuh"
+#include "shard.cuh"
 
 using namespace lm;
 
@@ -136,13 +137,17 @@ struct lm_engine {
   int device = 0, B = 0, num_sms = 0;
   cudaStream_t st = nullptr;
   void* act[NUM_ACT] = {};  // split buffers: op_t planes; "L" buffers: fp32
+  ShardView shard;             // multi-GPU slice sharding (lm_shard_*): gather blocks of all ranks
+  bool shard_connected = false;
+  uint32_t shard_epoch = 0;
+  uint32_t* h_shard_err = nullptr;  // pinned copy of the block's error word
   int32_t* d_spare = nullptr;  // device int32[16]: spare label values computed on the device (fusion, mask.py:228)
   int* d_range = nullptr;   // device flag: a value left the operand format's range (fp16 build: |x| > 65504)
   int* h_range = nullptr;   // pinned host copy, refreshed at the end of every forward
   Slot slots[LM_MAX_SLOTS];
   DevBuf<int16_t> d_vol, d_resized;
   DevBuf<int32_t> d_boxes;
-  DevBuf<uint8_t> d_labels, d_post, d_out, d_out2, d_mask;
+  DevBuf<uint8_t> d_labels, d_post, d_out, d_out2, d_fused, d_mask;
   DevBuf<float> d_scores;
   DevBuf<uint32_t> d_scratch;
   PostScratch post;
@@ -158,6 +163,7 @@ struct lm_engine {
   int dual_issue = 0;     // 1: two MMA-issuing threads per CTA on alternate chunks (conv_tc.cu)
   int cta_pairs = 0;      // 1: the experimental cta_group::2 kernel (conv_tc_pair.cu; not validated on hardware yet)
   int stem_v2 = 0;        // 1: stem_kernel_v2 (forward_misc.cu; not validated on hardware yet)
+  int upsample_v2 = 0;    // 1: upsample2x_cells_kernel (forward_misc.cu: one load per output sample)
   int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
   int chunk_kb_wide = 2;  // ... for the layers with Cout >= 128 (ring of 2 slots: chunk 1 leaves the tensor pipe waiting
                           // for the drain; chunk 2 costs < 1e-5 of score accuracy there, tools/debug_gpu.py)
@@ -226,8 +232,8 @@ int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_
     e->launches++;
     if (up < 4 && UPS[up].after_layer == i) {
       const ActSpec& src = ACT[UPS[up].src];
-      RC(launch_upsample2x(static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n, R >> src.level, R >> src.level, src.C,
-                           e->d_range, e->num_sms, e->st));
+      RC((e->upsample_v2 ? launch_upsample2x_cells : launch_upsample2x)(static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n,
+                                                                      R >> src.level, R >> src.level, src.C, e->d_range, e->num_sms, e->st));
       e->launches++;
       ++up;
     }
@@ -330,6 +336,77 @@ int run_checked(lm_engine* e, F&& enqueue) {
   }
 }
 
+void shard_release(lm_engine* e) {
+  for (int p = 0; p < e->shard.world; ++p) {
+    if (!e->shard.block[p]) continue;
+    if (p == e->shard.rank) cudaFree(e->shard.block[p]); else cudaIpcCloseMemHandle(e->shard.block[p]);
+    e->shard.block[p] = nullptr;
+  }
+  if (e->h_shard_err) cudaFreeHost(e->h_shard_err);
+  e->h_shard_err = nullptr;
+  e->shard = ShardView();
+  e->shard_connected = false;
+}
+
+void shard_range(int S, int rank, int world, int* lo, int* hi) {
+  const int per = (S + world - 1) / world;
+  *lo = rank * per < S ? rank * per : S;
+  *hi = *lo + per < S ? *lo + per : S;
+}
+
+// One volume, slices sharded over the ranks: per-slice stages on this rank's slab, results written straight into the
+// rank's gather block, pushed to the peers, post-processing + reshape replicated on the gathered volume.
+// d_vol / d_out: WHOLE volume on this rank's device (only the slab of d_vol is read).
+int sharded_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
+  const ShardView& v = e->shard;
+  if (slot < 0 || slot >= LM_MAX_SLOTS || !e->slots[slot].loaded) return fail(-30, "weight slot %d not loaded", slot);
+  int lo, hi;
+  shard_range(S, v.rank, v.world, &lo, &hi);
+  const size_t plane = (size_t)H * W, rr = (size_t)R * R;
+  uint8_t* labels_full = v.block[v.rank] + shard_labels_offset(v.slice_cap);
+  int32_t* boxes_full = reinterpret_cast<int32_t*>(v.block[v.rank] + shard_boxes_offset());
+  const uint32_t epoch = ++e->shard_epoch;
+  const int ns = hi - lo;
+  CU(cudaEventRecord(e->ev[1], e->st));
+  if (ns > 0) {
+    RC(e->d_resized.reserve((size_t)ns * rr));
+    RC(launch_bodymask(d_vol + (size_t)lo * plane, ns, H, W, boxes_full + 4 * (size_t)lo, nullptr, e->num_sms, e->st));
+    RC(launch_resize(d_vol + (size_t)lo * plane, ns, H, W, boxes_full + 4 * (size_t)lo, e->d_resized.p, R, R, 1, e->num_sms, e->st));
+    e->launches += 2;
+  }
+  CU(cudaEventRecord(e->ev[2], e->st));
+  if (ns > 0) RC(forward_all(e, slot, e->d_resized.p, ns, labels_full + (size_t)lo * rr, nullptr, nullptr));
+  CU(cudaEventRecord(e->ev[3], e->st));
+  // the collective: wait until the peers have consumed the previous volume, push the slab, wait for theirs
+  RC(launch_shard_wait_done(v, epoch, e->st));
+  RC(launch_shard_push(v, (size_t)lo, (size_t)hi, rr, epoch, e->num_sms, e->st));
+  RC(launch_shard_wait_ready(v, epoch, e->st));
+  e->launches += v.world > 1 ? 3 : 0;
+  const uint8_t* masks = labels_full;
+  if (!(flags & LM_FLAG_NO_POSTPROCESS)) {
+    RC(e->d_post.reserve((size_t)S * rr));
+    RC(postprocess_device(e->post, labels_full, S, R, R, nullptr, 0, nullptr, 0, 3, e->slots[slot].K - 1, e->d_post.p, e->num_sms, e->st,
+                          &e->launches));
+    masks = e->d_post.p;
+  }
+  CU(cudaEventRecord(e->ev[4], e->st));
+  RC(reshape_device(masks, boxes_full, S, H, W, R, R, d_out, e->num_sms, e->st));
+  RC(launch_shard_signal_done(v, epoch, e->st));
+  e->launches += v.world > 1 ? 2 : 1;
+  CU(cudaEventRecord(e->ev[5], e->st));
+  CU(cudaMemcpyAsync(e->h_shard_err, shard_error_word(v), sizeof(uint32_t), cudaMemcpyDeviceToHost, e->st));
+  return 0;
+}
+
+int shard_check(lm_engine* e) {
+  if (e->h_shard_err && *e->h_shard_err) {
+    *e->h_shard_err = 0;
+    cudaMemsetAsync(shard_error_word(e->shard), 0, sizeof(uint32_t), e->st);
+    return fail(-50, "sharded gather: a peer rank did not arrive within the wait limit (rank %d of %d)", e->shard.rank, e->shard.world);
+  }
+  return 0;
+}
+
 void collect_timings(lm_engine* e) {
   if (e->time_convs) drain_conv_events(e);
   for (int i = 0; i < 6; ++i) {
@@ -372,6 +449,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
   if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
+  if (const char* c = getenv("LM_UPSAMPLE_V2")) e->upsample_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
   CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
@@ -397,6 +475,7 @@ void lm_destroy(lm_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
   for (int a = 0; a < NUM_ACT; ++a) cudaFree(e->act[a]);
+  shard_release(e);
   cudaFree(e->d_range);
   cudaFree(e->d_spare);
   cudaFreeHost(e->h_range);
@@ -405,7 +484,7 @@ void lm_destroy(lm_engine* e) {
     for (auto& l : s.lw) { cudaFree(l.w); cudaFree(l.bias); cudaFree(l.scale); cudaFree(l.shift); }
   }
   e->d_vol.release(); e->d_resized.release(); e->d_boxes.release(); e->d_labels.release(); e->d_post.release();
-  e->d_out.release(); e->d_out2.release(); e->d_mask.release(); e->d_scores.release(); e->d_scratch.release();
+  e->d_out.release(); e->d_out2.release(); e->d_fused.release(); e->d_mask.release(); e->d_scores.release(); e->d_scratch.release();
   e->post.release();
   for (auto& ev : e->ev) cudaEventDestroy(ev);
   for (auto& ev : e->ev_conv) cudaEventDestroy(ev);
@@ -523,34 +602,170 @@ int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, in
   return check_range(e);
 }
 
+// LMInferer.apply with a fill model on a device-resident volume: res_l / res_r in engine buffers, result to d_final
+static int fused_enqueue(lm_engine* e, int slot_base, int slot_fill, const int16_t* d_vol, int S, int H, int W, int flags,
+                         uint8_t* d_final) {
+  // both inner inferences honour volume_postprocessing (mask.py:191-194); the fusion post-processing below does not
+  const int inner = flags & LM_FLAG_NO_POSTPROCESS;
+  const size_t n = (size_t)S * H * W;
+  RC(inference_dev(e, slot_base, d_vol, S, H, W, inner, e->d_out.p));   // res_l (mask.py:225)
+  RC(inference_dev(e, slot_fill, d_vol, S, H, W, inner, e->d_out2.p));  // res_r (mask.py:227)
+  RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, e->d_spare, e->num_sms, e->st));  // spare stays on the device
+  e->launches += 3;
+  // labels after the fusion are <= K_base (the spare value is max + 1 <= K_base): mask.py:232
+  RC(postprocess_device(e->post, e->d_out.p, S, H, W, nullptr, 0, e->d_spare, 1, 3, e->slots[slot_base].K, d_final, e->num_sms, e->st,
+                        &e->launches));
+  return 0;
+}
+
 int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
   if (!e || !vol || !out) return fail(-1, "lm_apply_fused: NULL argument");
   if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_fused: empty volume");
+  if (slot_base < 0 || slot_base >= LM_MAX_SLOTS || !e->slots[slot_base].loaded) return fail(-30, "weight slot %d not loaded", slot_base);
   CU(cudaSetDevice(e->device));
   const size_t n = (size_t)S * H * W;
   RC(e->d_vol.reserve(n));
   RC(e->d_out.reserve(n));
   RC(e->d_out2.reserve(n));
-  if (slot_base < 0 || slot_base >= LM_MAX_SLOTS || !e->slots[slot_base].loaded) return fail(-30, "weight slot %d not loaded", slot_base);
+  RC(e->d_fused.reserve(n));
   RC(run_checked(e, [&]() -> int {
     e->launches = 0;
     e->ev_used = 0;
     CU(cudaEventRecord(e->ev[0], e->st));
     CU(cudaMemcpyAsync(e->d_vol.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
-    // both inner inferences honour volume_postprocessing (mask.py:191-194); the fusion post-processing below does not
-    const int inner = flags & LM_FLAG_NO_POSTPROCESS;
-    RC(inference_dev(e, slot_base, e->d_vol.p, S, H, W, inner, e->d_out.p));   // res_l (mask.py:225)
-    RC(inference_dev(e, slot_fill, e->d_vol.p, S, H, W, inner, e->d_out2.p));  // res_r (mask.py:227)
-    RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, e->d_spare, e->num_sms, e->st));  // spare stays on the device
-    e->launches += 3;
-    // labels after the fusion are <= K_base (the spare value is max + 1 <= K_base): mask.py:232
-    RC(postprocess_device(e->post, e->d_out.p, S, H, W, nullptr, 0, e->d_spare, 1, 3, e->slots[slot_base].K, e->d_out2.p, e->num_sms,
-                          e->st, &e->launches));
-    CU(cudaMemcpyAsync(out, e->d_out2.p, n, cudaMemcpyDeviceToHost, e->st));
+    RC(fused_enqueue(e, slot_base, slot_fill, e->d_vol.p, S, H, W, flags, e->d_fused.p));
+    CU(cudaMemcpyAsync(out, e->d_fused.p, n, cudaMemcpyDeviceToHost, e->st));
     CU(cudaEventRecord(e->ev[6], e->st));
     return 0;
   }));
   collect_timings(e);
+  return check_range(e);
+}
+
+int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
+  if (!e || !d_vol || !d_out) return fail(-1, "lm_apply_fused_dev: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_fused_dev: empty volume");
+  if (slot_base < 0 || slot_base >= LM_MAX_SLOTS || !e->slots[slot_base].loaded) return fail(-30, "weight slot %d not loaded", slot_base);
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W;
+  RC(e->d_out.reserve(n));
+  RC(e->d_out2.reserve(n));
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    RC(fused_enqueue(e, slot_base, slot_fill, d_vol, S, H, W, flags, d_out));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
+  collect_timings(e);
+  return check_range(e);
+}
+
+int lm_shard_init(lm_engine* e, int rank, int world, int max_slices) {
+  if (!e) return fail(-1, "lm_shard_init: NULL engine");
+  if (world < 1 || world > kShardMaxWorld || rank < 0 || rank >= world) return fail(-1, "lm_shard_init: rank %d / world %d", rank, world);
+  if (max_slices < 1) return fail(-1, "lm_shard_init: max_slices < 1");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->st));
+  shard_release(e);
+  e->shard.rank = rank; e->shard.world = world;
+  const size_t per = ((size_t)max_slices + world - 1) / world;
+  e->shard.slice_cap = per * world;
+  e->shard.block_bytes = shard_block_bytes(e->shard.slice_cap, (size_t)R * R);
+  void* p = nullptr;
+  CU(cudaMalloc(&p, e->shard.block_bytes));
+  e->shard.block[rank] = static_cast<uint8_t*>(p);
+  CU(cudaMemset(p, 0, e->shard.block_bytes));
+  CU(cudaMallocHost(&e->h_shard_err, sizeof(uint32_t)));
+  *e->h_shard_err = 0;
+  e->shard_epoch = 0;
+  e->shard_connected = (world == 1);
+  return 0;
+}
+
+size_t lm_shard_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+int lm_shard_export(lm_engine* e, void* handle_out) {
+  if (!e || !handle_out) return fail(-1, "lm_shard_export: NULL argument");
+  if (!e->shard.block[e->shard.rank]) return fail(-51, "lm_shard_export: call lm_shard_init first");
+  CU(cudaSetDevice(e->device));
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, e->shard.block[e->shard.rank]));
+  memcpy(handle_out, &h, sizeof(h));
+  return 0;
+}
+
+int lm_shard_connect(lm_engine* e, const void* handles) {
+  if (!e || !handles) return fail(-1, "lm_shard_connect: NULL argument");
+  if (!e->shard.block[e->shard.rank]) return fail(-51, "lm_shard_connect: call lm_shard_init first");
+  CU(cudaSetDevice(e->device));
+  const uint8_t* hb = static_cast<const uint8_t*>(handles);
+  for (int p = 0; p < e->shard.world; ++p) {
+    if (p == e->shard.rank || e->shard.block[p]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hb + (size_t)p * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    e->shard.block[p] = static_cast<uint8_t*>(ptr);
+  }
+  e->shard_connected = true;
+  return 0;
+}
+
+int lm_shard_labels(lm_engine* e, void** d_boxes, void** d_labels, size_t* slice_cap) {
+  if (!e) return fail(-1, "lm_shard_labels: NULL engine");
+  if (!e->shard.block[e->shard.rank]) return fail(-51, "lm_shard_labels: call lm_shard_init first");
+  if (d_boxes) *d_boxes = e->shard.block[e->shard.rank] + shard_boxes_offset();
+  if (d_labels) *d_labels = e->shard.block[e->shard.rank] + shard_labels_offset(e->shard.slice_cap);
+  if (slice_cap) *slice_cap = e->shard.slice_cap;
+  return 0;
+}
+
+int lm_apply_volume_sharded_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
+  if (!e || !d_vol || !d_out) return fail(-1, "lm_apply_volume_sharded_dev: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_volume_sharded_dev: empty volume");
+  if (!e->shard_connected) return fail(-51, "lm_apply_volume_sharded_dev: call lm_shard_init / lm_shard_connect first");
+  if ((size_t)S > e->shard.slice_cap) return fail(-52, "lm_apply_volume_sharded_dev: %d slices exceed the gather capacity %zu", S, e->shard.slice_cap);
+  CU(cudaSetDevice(e->device));
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    RC(sharded_dev(e, slot, d_vol, S, H, W, flags, d_out));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
+  collect_timings(e);
+  RC(shard_check(e));
+  return check_range(e);
+}
+
+int lm_apply_volume_sharded(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
+  if (!e || !vol) return fail(-1, "lm_apply_volume_sharded: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_volume_sharded: empty volume");
+  if (!e->shard_connected) return fail(-51, "lm_apply_volume_sharded: call lm_shard_init / lm_shard_connect first");
+  if ((size_t)S > e->shard.slice_cap) return fail(-52, "lm_apply_volume_sharded: %d slices exceed the gather capacity %zu", S, e->shard.slice_cap);
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W, plane = (size_t)H * W;
+  RC(e->d_vol.reserve(n));
+  RC(e->d_out.reserve(n));
+  int lo, hi;
+  shard_range(S, e->shard.rank, e->shard.world, &lo, &hi);
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    if (hi > lo)  // only this rank's slab crosses the PCIe bus
+      CU(cudaMemcpyAsync(e->d_vol.p + (size_t)lo * plane, vol + (size_t)lo * plane, (size_t)(hi - lo) * plane * sizeof(int16_t),
+                         cudaMemcpyHostToDevice, e->st));
+    RC(sharded_dev(e, slot, e->d_vol.p, S, H, W, flags, e->d_out.p));
+    if (out) CU(cudaMemcpyAsync(out, e->d_out.p, n, cudaMemcpyDeviceToHost, e->st));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
+  collect_timings(e);
+  RC(shard_check(e));
   return check_range(e);
 }
 
@@ -717,6 +932,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
   if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
+  if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value != 0; return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
   if (!strcmp(key, "post_region_capacity")) {  // test hook: shrink / grow the region tables (exercises the overflow re-run)
     if (value < 1) return fail(-1, "post_region_capacity must be >= 1");

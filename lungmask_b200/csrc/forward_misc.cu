@@ -166,6 +166,13 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict_
   if (ovf && range_flag) *range_flag = 1;
 }
 
+// One bilinear sample with a fixed operation order (explicit fused multiply-adds: both upsample kernels round alike)
+__device__ __forceinline__ float bilerp(float p00, float p01, float p10, float p11, float lx0, float lx1, float ly0, float ly1) {
+  const float top = __fmaf_rn(lx1, p01, __fmul_rn(lx0, p00));
+  const float bot = __fmaf_rn(lx1, p11, __fmul_rn(lx0, p10));
+  return __fmaf_rn(ly1, bot, __fmul_rn(ly0, top));
+}
+
 // in: [N][h][w][C] fp32 -> out: [N][2][2h][2w][C] split planes. PyTorch semantics (align_corners=False):
 // src = max(0.5*(dst+0.5)-0.5, 0), i0 = (int)src, i1 = i0 + (i0 < size-1), l1 = src - i0, l0 = 1 - l1.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, op_t* __restrict__ out,
@@ -193,12 +200,83 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
       const float4 p01 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x1) * C) + q);
       const float4 p10 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x0) * C) + q);
       const float4 p11 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x1) * C) + q);
-#define LM_BILERP(f, e) vv[4 * q + e] = ly0 * (lx0 * p00.f + lx1 * p01.f) + ly1 * (lx0 * p10.f + lx1 * p11.f);
+#define LM_BILERP(f, e) vv[4 * q + e] = bilerp(p00.f, p01.f, p10.f, p11.f, lx0, lx1, ly0, ly1);
       LM_BILERP(x, 0) LM_BILERP(y, 1) LM_BILERP(z, 2) LM_BILERP(w, 3)
 #undef LM_BILERP
     }
     op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
     split_store(vv, o, o + oplane * C, ovf);
+  }
+  if (ovf && range_flag) *range_flag = 1;
+}
+
+// upsample2x_cells_kernel: the same samples from a cell-centred work assignment.  With scale 2 and align_corners=False
+// the output rows 2i+1 and 2i+2 both interpolate between input rows i and i+1 (weights 0.75/0.25 and 0.25/0.75; the
+// frame rows 0 and 2h-1 take weight 1/0 and a clamped partner), and likewise for columns: a thread owns the CELL between
+// input pixels (i, j) and (i+1, j+1), i in [-1, h-1], j in [-1, w-1], loads its four corners ONCE (CPT channels each) and
+// writes the (up to) 2 x 2 output pixels - 1 load per output instead of 4, and no 64-bit index arithmetic per output.
+// The per-row / per-column (index, weight) pairs are derived with upsample2x_kernel's own formula, so both kernels
+// produce identical bits.
+__device__ __forceinline__ void up_axis(int o, int n_in, int& i0, int& i1, float& l0, float& l1) {
+  const float s = fmaxf(0.5f * ((float)o + 0.5f) - 0.5f, 0.f);
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+__global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __restrict__ in, op_t* __restrict__ out,
+                                                               int N, int h, int w, int C, int* __restrict__ range_flag) {
+  const int cq_per_pix = C / CPT;
+  const int cw = w + 1, ch = h + 1;
+  const int H = 2 * h, W = 2 * w;
+  const size_t oplane = (size_t)H * W;
+  const size_t total = (size_t)N * ch * cw * cq_per_pix;
+  bool ovf = false;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cq = (int)(t % cq_per_pix);
+    size_t cell = t / cq_per_pix;
+    const int cj = (int)(cell % cw) - 1;
+    cell /= cw;
+    const int ci = (int)(cell % ch) - 1;
+    const int n = (int)(cell / ch);
+    const int ya = ci < 0 ? 0 : ci, yb = ya + 1 < h ? ya + 1 : h - 1;   // the two input rows / columns every sample of the
+    const int xa = cj < 0 ? 0 : cj, xb = xa + 1 < w ? xa + 1 : w - 1;   // cell interpolates between (frame cells: clamped)
+    const float* base = in + (size_t)n * h * w * C + cq * CPT;
+    float p[2][2][CPT];
+#pragma unroll
+    for (int q = 0; q < CPT / 4; ++q) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(base + ((size_t)ya * w + xa) * C) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(base + ((size_t)ya * w + xb) * C) + q);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yb * w + xa) * C) + q);
+      const float4 e = __ldg(reinterpret_cast<const float4*>(base + ((size_t)yb * w + xb) * C) + q);
+      p[0][0][4 * q] = a.x; p[0][0][4 * q + 1] = a.y; p[0][0][4 * q + 2] = a.z; p[0][0][4 * q + 3] = a.w;
+      p[0][1][4 * q] = b.x; p[0][1][4 * q + 1] = b.y; p[0][1][4 * q + 2] = b.z; p[0][1][4 * q + 3] = b.w;
+      p[1][0][4 * q] = c.x; p[1][0][4 * q + 1] = c.y; p[1][0][4 * q + 2] = c.z; p[1][0][4 * q + 3] = c.w;
+      p[1][1][4 * q] = e.x; p[1][1][4 * q + 1] = e.y; p[1][1][4 * q + 2] = e.z; p[1][1][4 * q + 3] = e.w;
+    }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int y = 2 * ci + 1 + dy;
+      if (y < 0 || y >= H) continue;
+      int y0, y1; float ly0, ly1;
+      up_axis(y, h, y0, y1, ly0, ly1);
+      const int ry0 = (y0 == ya) ? 0 : 1, ry1 = (y1 == ya) ? 0 : 1;   // which of the two loaded rows (ya <= yb)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int x = 2 * cj + 1 + dx;
+        if (x < 0 || x >= W) continue;
+        int x0, x1; float lx0, lx1;
+        up_axis(x, w, x0, x1, lx0, lx1);
+        const int rx0 = (x0 == xa) ? 0 : 1, rx1 = (x1 == xa) ? 0 : 1;
+        float vv[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e)
+          vv[e] = bilerp(p[ry0][rx0][e], p[ry0][rx1][e], p[ry1][rx0][e], p[ry1][rx1][e], lx0, lx1, ly0, ly1);
+        const size_t r = (size_t)y * W + x;
+        op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
+        split_store(vv, o, o + oplane * C, ovf);
+      }
+    }
   }
   if (ovf && range_flag) *range_flag = 1;
 }
@@ -252,6 +330,12 @@ int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bi
 int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream) {
   const size_t total = (size_t)N * 4 * h * w * (C / CPT);
   upsample2x_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag);
+  return (int)cudaGetLastError();
+}
+
+int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream) {
+  const size_t total = (size_t)N * (h + 1) * (w + 1) * (C / CPT);
+  upsample2x_cells_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag);
   return (int)cudaGetLastError();
 }
 

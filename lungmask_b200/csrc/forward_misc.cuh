@@ -14,6 +14,8 @@ int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bi
                    const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream);
 // fp32 [N][h][w][C] -> split planes [N][2][2h][2w][C]
 int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream);
+// same samples, one thread per cell between four input pixels (1 load per output instead of 4); see forward_misc.cu
+int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream);
 // OIHW fp32 -> [2][taps][Cout][Cin] hi/lo operand planes
 int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, cudaStream_t stream);
 }  // namespace lm

@@ -33,7 +33,7 @@ def setup(engine):
     return resized, _forward(engine, resized)
 
 
-@pytest.mark.parametrize("option", ["stem_v2", "cta_pairs"])
+@pytest.mark.parametrize("option", ["stem_v2", "upsample_v2", "cta_pairs"])
 def test_experimental_kernel_is_bit_identical(engine, setup, option):
     resized, (labels, scores) = setup
     l2, s2 = _forward(engine, resized, **{option: 1})

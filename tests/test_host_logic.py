@@ -61,6 +61,18 @@ def test_int16_conversion_rules():
         _to_int16_volume(np.zeros((4, 4), np.int16))
 
 
+def test_native_binding_refuses_lossy_conversions():
+    from lungmask_b200._native import _as
+    assert _as(np.array([[1, 2]], dtype=np.int64), np.int32).dtype == np.int32        # fits: converted
+    assert _as(np.array([True, False]), np.uint8).tolist() == [1, 0]
+    with pytest.raises(TypeError):
+        _as(np.array([40000], dtype=np.int32), np.int16)                                # would wrap
+    with pytest.raises(TypeError):
+        _as(np.array([1.5], dtype=np.float32), np.int16)                                # would truncate
+    with pytest.raises(ValueError):
+        _as(np.zeros((2, 2), np.int16), np.int16, 3)
+
+
 def test_cli_flags_match_reference():
     from lungmask_b200.__main__ import build_parser
     p = build_parser()
@@ -118,6 +130,44 @@ def test_two_rank_gloo_matches_single_rank():
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def _connect_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from lungmask_b200.parallel import connect
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class FakeEngine:  # records the collective protocol of lungmask_b200.parallel.connect
+        def shard_init(self, r, w, n):
+            self.init = (r, w, n)
+
+        def shard_export(self):
+            return bytes([rank]) * 64
+
+        def shard_connect(self, handles):
+            self.handles = handles
+
+    e = connect(FakeEngine(), rank, world, 300)
+    ok = e.init == (rank, world, 300) and e.handles == [bytes([r]) * 64 for r in range(world)]
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_shard_connect_exchanges_handles_in_rank_order():
+    """world_size-2 gloo run of the handle exchange behind the engine's device-side gather (csrc/shard.cu)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_connect_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]

@@ -15,7 +15,7 @@ tail -15 $O/pytest_experimental.log
 timeout 1200 python -m pytest tests -m gpu -q -s --durations=15 > $O/pytest_gpu_r2c1.log 2>&1; echo "pytest rc=$?"
 grep -E "passed|failed|error|Error|C2 |C3 |C4 |end to end|fused|golden|differing|max\|dscore" $O/pytest_gpu_r2c1.log | cut -c1-220 | tail -60
 timeout 300 python bench.py --steps 5 --warmup 3 > $O/bench_default.json 2> $O/bench_default.err; echo "bench rc=$?"
-for opt in LM_STEM_V2 LM_CTA_PAIRS; do
+for opt in LM_STEM_V2 LM_UPSAMPLE_V2 LM_CTA_PAIRS; do
   env $opt=1 timeout 300 python bench.py --steps 5 --warmup 3 > $O/bench_$opt.json 2> $O/bench_$opt.err; echo "$opt rc=$?"
 done
 LM_CCL_RULE=0 timeout 300 python bench.py --steps 5 --warmup 3 > $O/bench_LM_CCL_RULE0.json 2> $O/bench_LM_CCL_RULE0.err
