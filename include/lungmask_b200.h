@@ -13,9 +13,10 @@
  *
  * Numerics: the convolutions carry every fp32 value as an fp16 pair (hi + lo * 2^-11, 22 significant bits) on the
  * tensor cores and accumulate in fp32; results match the reference's fp32 forward within 1e-4 on the log-softmax
- * scores.  fp16 saturates at 65504: if a weight (lm_load_weights) or an activation (any call that runs the network)
- * leaves that range the call fails with LM_ERR_RANGE and the output must be discarded - it never returns a
- * silently wrong mask.
+ * scores.  fp16 saturates at 65504: every activation tensor and every layer's weights carry a power-of-two scale
+ * (exact: no significand changes); when a value would leave the range the engine lowers that tensor's scale and runs
+ * the forward again, transparently.  LM_ERR_RANGE remains only for non-finite weights and for activations beyond
+ * about 1e14 - it never returns a silently wrong mask.
  */
 #ifndef LUNGMASK_B200_H
 #define LUNGMASK_B200_H
@@ -38,7 +39,7 @@ typedef struct lm_engine lm_engine;
 #define LM_NET_RES 256           /* mask.py:166: utils.preprocess(..., resolution=[256, 256]) */
 #define LM_MAX_SLOTS 4           /* weight slots (e.g. 0 = base model, 1 = fill model) */
 #define LM_FLAG_NO_POSTPROCESS 1 /* LMInferer(volume_postprocessing=False), mask.py:191-194 */
-#define LM_ERR_RANGE (-40)       /* a weight / activation exceeded the fp16 operand range (see "Numerics") */
+#define LM_ERR_RANGE (-40)       /* non-finite weight, or an activation beyond every representable scale (see "Numerics") */
 
 /* Engine lifetime.  Replaces LMInferer.__init__'s device pick + model.to(device), mask.py:118-139.
  * batch_capacity = slices per forward wave (the reference's batch_size only bounds memory, results

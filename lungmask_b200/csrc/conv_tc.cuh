@@ -12,7 +12,8 @@
 //                at twice the tf32 rate and moves half the bytes.  The scaled low half keeps the residuals
 //                of small values out of the fp16 subnormal range; the hi*lo + lo*hi accumulator is multiplied
 //                by 2^-11 when it is read.  fp16 saturates at 65504: the epilogues raise ConvParams::range_flag
-//                when a value leaves that range and the engine reports an error instead of a wrong mask.
+//                when a value leaves that range; the engine then lowers that tensor's power-of-two scale
+//                (ConvParams::out_scale) and runs the forward again - exact, and never a wrong mask.
 //   0            tf32 pairs, kind::tf32 (round 1's first scheme; no range limit, half the throughput).
 #ifndef LM_OPERAND_F16
 #define LM_OPERAND_F16 1
@@ -59,6 +60,11 @@ struct ConvParams {
   void* out;          // mode 0/1: op_t [N][2][H][W][Cout]; mode 2: fp32 [N][H][W][Cout]; mode 3: unused
   void* out_pool;     // mode 1: op_t [N][2][H/2][W/2][Cout]
   int* range_flag;    // set to 1 when an output leaves the operand format's range (fp16 build); may be nullptr
+  // Power-of-two range management (exact: a power of two changes no significand).  The operand planes of a tensor hold
+  // value * act_scale, weights hold w * w_scale; the epilogue multiplies the accumulator by in_unscale =
+  // 1 / (act_scale(in) * w_scale) before the bias and stores y * out_scale.  All 1.0 unless the engine had to move a
+  // tensor's range below fp16's 65504 (engine.cu: range_finish); 1.0 multiplications leave every bit as it was.
+  float in_unscale, out_scale;
   const float* head_w;  // mode 3: [K][Cout]
   const float* head_b;  // mode 3: [K]
   int K;                // mode 3: classes (<= 8)

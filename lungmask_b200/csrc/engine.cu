@@ -115,6 +115,7 @@ struct UpSpec { int after_layer, src, dst; };
 const UpSpec UPS[4] = {{9, L0, U0}, {12, L1, U1}, {15, L2, U2}, {18, L3, U3}};
 
 struct LayerWeights {
+  float w_scale = 1.f;  // power of two: the planes hold w * w_scale, normalised to max |w * w_scale| in (2^14, 2^15]
   void* w = nullptr;  // op_t [2][taps][Cout][Cin] split
   float* bias = nullptr;
   float* scale = nullptr;
@@ -128,7 +129,23 @@ struct Slot {
   float *head_w = nullptr, *head_b = nullptr;
   ConvMaps maps[NUM_LAYERS];
   ConvParams params[NUM_LAYERS];
+  // Power-of-two scale of every split-plane activation tensor (conv_tc.cuh ConvParams::out_scale): all 1 until a value
+  // of that tensor left fp16's range in some forward; then range_finish lowers the tensor's scale by 2^-8 (exactly
+  // representable, no significand changes) and the forward runs again.  The state sticks to the weights it was found for.
+  float act_scale[NUM_ACT];
+  Slot() { for (float& s : act_scale) s = 1.f; }
 };
+// Tensors that feed one convolution together (virtual concat) or leave one epilogue together (block output + its
+// pooled copy) share a scale: skip S_i, pooled P_i and the upsampled U_{3-i}.
+int scale_group(int a) {
+  switch (a) {
+    case S0: case P0: case U3: return S0;
+    case S1: case P1: case U2: return S1;
+    case S2: case P2: case U1: return S2;
+    case S3: case P3: case U0: return S3;
+    default: return a;
+  }
+}
 
 }  // namespace lm_impl
 using namespace lm_impl;
@@ -142,8 +159,11 @@ struct lm_engine {
   uint32_t shard_epoch = 0;
   uint32_t* h_shard_err = nullptr;  // pinned copy of the block's error word
   int32_t* d_spare = nullptr;  // device int32[16]: spare label values computed on the device (fusion, mask.py:228)
-  int* d_range = nullptr;   // device flag: a value left the operand format's range (fp16 build: |x| > 65504)
+  int* d_range = nullptr;   // device flags [NUM_ACT + 1]: a value of activation tensor a (or, last entry, a weight) left the
+                            // operand format's range (fp16 build: |x * scale| > 65504)
   int* h_range = nullptr;   // pinned host copy, refreshed at the end of every forward
+  int range_slot = -1;      // the slot whose forward the flags belong to
+  int range_retries = 0;
   Slot slots[LM_MAX_SLOTS];
   DevBuf<int16_t> d_vol, d_resized;
   DevBuf<int32_t> d_boxes;
@@ -211,14 +231,17 @@ int upload(float** dst, const float* src, size_t n, cudaStream_t st) {
 int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_t* d_labels, float* d_scores,
                   bool time_convs) {
   RC((e->stem_v2 ? launch_stem_v2 : launch_stem)(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
-                                                 e->d_range, e->num_sms, e->st));
+                                                 e->d_range + A0, s.act_scale[A0], e->num_sms, e->st));
   e->launches++;
   int up = 0;
   for (int i = 0; i < NUM_LAYERS; ++i) {
     ConvParams p = s.params[i];
     p.N = n;
     p.chunk_kb = (p.Cout >= 128) ? e->chunk_kb_wide : e->chunk_kb;
-    p.range_flag = e->d_range;
+    const LayerSpec& L = LAYERS[i];
+    p.range_flag = L.dst >= 0 ? e->d_range + L.dst : nullptr;
+    p.in_unscale = 1.f / (s.act_scale[L.src0] * s.lw[i].w_scale);   // src1 (virtual concat) shares src0's scale group
+    p.out_scale = (L.mode == kModeReluBn || L.mode == kModeReluBnPool) ? s.act_scale[L.dst] : 1.f;
     p.dual_issue = e->dual_issue;
     if (p.mode == kModeHead) { p.labels = d_labels; p.scores = d_scores; }
     if (time_convs) {
@@ -233,7 +256,8 @@ int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_
     if (up < 4 && UPS[up].after_layer == i) {
       const ActSpec& src = ACT[UPS[up].src];
       RC((e->upsample_v2 ? launch_upsample2x_cells : launch_upsample2x)(static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n,
-                                                                      R >> src.level, R >> src.level, src.C, e->d_range, e->num_sms, e->st));
+                                                                      R >> src.level, R >> src.level, src.C, e->d_range + UPS[up].dst,
+                                                                      s.act_scale[UPS[up].dst], e->num_sms, e->st));
       e->launches++;
       ++up;
     }
@@ -273,7 +297,8 @@ int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t
       CU(cudaStreamSynchronize(e->st));
     }
   }
-  CU(cudaMemcpyAsync(e->h_range, e->d_range, sizeof(int), cudaMemcpyDeviceToHost, e->st));  // read by check_range after the caller's sync
+  CU(cudaMemcpyAsync(e->h_range, e->d_range, (NUM_ACT + 1) * sizeof(int), cudaMemcpyDeviceToHost, e->st));  // read by range_finish after the caller's sync
+  e->range_slot = slot;
   if (conv_ms) {  // device time of the tensor-core convolution launches alone (CUDA events on the launch stream)
     CU(cudaStreamSynchronize(e->st));
     RC(drain_conv_events(e));
@@ -311,14 +336,31 @@ int inference_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, in
 }
 
 // After a stream synchronisation: did any activation leave the operand format's range during the forward passes?
-int check_range(lm_engine* e) {
-  if (*e->h_range) {
-    *e->h_range = 0;
-    cudaMemsetAsync(e->d_range, 0, sizeof(int), e->st);
-    return fail(LM_ERR_RANGE, "an activation exceeded the fp16 operand range (|x| > 65504); the result is invalid "
-                     "(rebuild with -DLM_OPERAND_F16=0 for the tf32 operand format)");
+// Returns 0 (no), 1 (yes: the offending tensors' power-of-two scales were lowered - run the forward again) or an error.
+int range_finish(lm_engine* e) {
+  bool any = false;
+  for (int a = 0; a <= NUM_ACT; ++a) any |= e->h_range[a] != 0;
+  if (!any) { e->range_retries = 0; return 0; }
+  cudaMemsetAsync(e->d_range, 0, (NUM_ACT + 1) * sizeof(int), e->st);
+  const bool weight_flag = e->h_range[NUM_ACT] != 0;
+  bool flagged[NUM_ACT] = {};
+  for (int a = 0; a < NUM_ACT; ++a) { flagged[a] = e->h_range[a] != 0; e->h_range[a] = 0; }
+  e->h_range[NUM_ACT] = 0;
+  if (weight_flag || e->range_slot < 0 || e->range_slot >= LM_MAX_SLOTS || ++e->range_retries > 4) {
+    e->range_retries = 0;
+    return fail(LM_ERR_RANGE, "an activation exceeded the fp16 operand range even after rescaling by 2^-32 (|x| > 2.8e14): "
+                              "the weights are not a usable network (rebuild with -DLM_OPERAND_F16=0 for tf32 operands)");
   }
-  return 0;
+  Slot& s = e->slots[e->range_slot];
+  for (int a = 0; a < NUM_ACT; ++a) {
+    if (!flagged[a]) continue;
+    const int g = scale_group(a);
+    for (int b = 0; b < NUM_ACT; ++b)
+      if (scale_group(b) == g && s.act_scale[b] > 1e-30f) s.act_scale[b] *= (1.f / 256.f);
+    for (int b = 0; b < NUM_ACT; ++b)   // one step per group and retry, whichever member raised the flag
+      if (scale_group(b) == g) flagged[b] = false;
+  }
+  return 1;
 }
 
 // Enqueue-synchronise-verify: `enqueue` puts a whole call on the engine stream; after the synchronisation the
@@ -330,9 +372,12 @@ int run_checked(lm_engine* e, F&& enqueue) {
   for (int attempt = 0;; ++attempt) {
     RC(enqueue());
     CU(cudaStreamSynchronize(e->st));
-    if (!postprocess_finish(e->post)) return 0;
-    if (attempt >= 2) return fail(-22, "post-processing: region tables overflowed repeatedly (%u regions)", e->post.last_regions);
-    RC(e->post.reserve_regions(e->post.want_regions));
+    const int rr = range_finish(e);   // 1: a tensor left fp16's range, its scale was lowered -> run again (exact rescale)
+    if (rr < 0) return rr;
+    const int pf = postprocess_finish(e->post);
+    if (!rr && !pf) return 0;
+    if (attempt >= 8) return fail(-22, "the call did not settle after %d re-runs (region tables %u regions / operand range)", attempt, e->post.last_regions);
+    if (pf) RC(e->post.reserve_regions(e->post.want_regions));
   }
 }
 
@@ -461,10 +506,10 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
     CU(cudaMalloc(&e->act[a], ACT[a].split ? elems * 2 * sizeof(op_t) : elems * sizeof(float)));
   }
   CU(cudaMalloc(&e->d_spare, 16 * sizeof(int32_t)));
-  CU(cudaMalloc(&e->d_range, sizeof(int)));
-  CU(cudaMemset(e->d_range, 0, sizeof(int)));
-  CU(cudaMallocHost(&e->h_range, sizeof(int)));
-  *e->h_range = 0;
+  CU(cudaMalloc(&e->d_range, (NUM_ACT + 1) * sizeof(int)));
+  CU(cudaMemset(e->d_range, 0, (NUM_ACT + 1) * sizeof(int)));
+  CU(cudaMallocHost(&e->h_range, (NUM_ACT + 1) * sizeof(int)));
+  memset(e->h_range, 0, (NUM_ACT + 1) * sizeof(int));
   RC(e->d_scratch.reserve(64));
   *out = e;
   return 0;
@@ -520,9 +565,24 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
     const LayerSpec& L = LAYERS[i];
     const int Cin = L.C0 + L.C1;
     const size_t nw = (size_t)L.Cout * Cin * L.taps;
+    // power-of-two weight scale (undone, exactly, by ConvParams::in_unscale); non-finite weights are refused
+    float wmax = 0.f;
+    for (size_t k = 0; k < nw; ++k) {
+      const float a = fabsf(q[k]);
+      if (!(a <= 3.0e38f)) return fail(LM_ERR_RANGE, "lm_load_weights: layer %d holds a non-finite weight", i);
+      wmax = a > wmax ? a : wmax;
+    }
+    // normalise the layer to the top of the operand format's range, max |w| * ws in (2^14, 2^15]: the hi / lo planes then
+    // keep their 11 + 11 bits for every weight down to 2^-28 of the largest one, whatever the layer's magnitude
+    float ws = 1.f;
+    if (wmax > 0.f) {
+      while (wmax * ws > 32768.f) ws *= 0.5f;
+      while (wmax * ws <= 16384.f && ws < 1.0e30f) ws *= 2.f;
+    }
+    s.lw[i].w_scale = ws;
     CU(cudaMemcpyAsync(d_tmp, q, nw * sizeof(float), cudaMemcpyHostToDevice, e->st)); q += nw;
     if (!s.lw[i].w) CU(cudaMalloc(&s.lw[i].w, 2 * nw * sizeof(op_t)));
-    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->d_range, e->st));
+    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->d_range + NUM_ACT, ws, e->st));
     CU(cudaStreamSynchronize(e->st));
     RC(upload(&s.lw[i].bias, q, L.Cout, e->st)); q += L.Cout;
     if (has_bn) {
@@ -541,13 +601,14 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   RC(upload(&s.head_w, q, (size_t)K * 64, e->st)); q += (size_t)K * 64;
   RC(upload(&s.head_b, q, K, e->st)); q += K;
   if ((size_t)(q - blob) != n_floats) return fail(-1, "lm_load_weights: internal blob walk mismatch");
-  CU(cudaMemcpyAsync(e->h_range, e->d_range, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(e->h_range + NUM_ACT, e->d_range + NUM_ACT, sizeof(int), cudaMemcpyDeviceToHost, e->st));
   CU(cudaStreamSynchronize(e->st));
-  if (*e->h_range) {
-    *e->h_range = 0;
-    CU(cudaMemsetAsync(e->d_range, 0, sizeof(int), e->st));
-    return fail(LM_ERR_RANGE, "lm_load_weights: a convolution weight exceeds the fp16 operand range (|w| > 65504)");
+  if (e->h_range[NUM_ACT]) {
+    e->h_range[NUM_ACT] = 0;
+    CU(cudaMemsetAsync(e->d_range + NUM_ACT, 0, sizeof(int), e->st));
+    return fail(LM_ERR_RANGE, "lm_load_weights: a scaled convolution weight still exceeds the fp16 operand range (internal error)");
   }
+  for (float& sc : s.act_scale) sc = 1.f;   // new weights: activation ranges are unknown again
   for (int i = 0; i < NUM_LAYERS; ++i) {
     const LayerSpec& L = LAYERS[i];
     ConvParams p{};
@@ -578,7 +639,7 @@ int lm_apply_volume_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int
     return 0;
   }));
   collect_timings(e);
-  return check_range(e);
+  return 0;
 }
 
 int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
@@ -599,7 +660,7 @@ int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, in
     return 0;
   }));
   collect_timings(e);
-  return check_range(e);
+  return 0;
 }
 
 // LMInferer.apply with a fill model on a device-resident volume: res_l / res_r in engine buffers, result to d_final
@@ -639,7 +700,7 @@ int lm_apply_fused(lm_engine* e, int slot_base, int slot_fill, const int16_t* vo
     return 0;
   }));
   collect_timings(e);
-  return check_range(e);
+  return 0;
 }
 
 int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
@@ -659,7 +720,7 @@ int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const int16_t
     return 0;
   }));
   collect_timings(e);
-  return check_range(e);
+  return 0;
 }
 
 int lm_shard_init(lm_engine* e, int rank, int world, int max_slices) {
@@ -737,8 +798,7 @@ int lm_apply_volume_sharded_dev(lm_engine* e, int slot, const int16_t* d_vol, in
     return 0;
   }));
   collect_timings(e);
-  RC(shard_check(e));
-  return check_range(e);
+  return shard_check(e);
 }
 
 int lm_apply_volume_sharded(lm_engine* e, int slot, const int16_t* vol, int S, int H, int W, int flags, uint8_t* out) {
@@ -765,8 +825,7 @@ int lm_apply_volume_sharded(lm_engine* e, int slot, const int16_t* vol, int S, i
     return 0;
   }));
   collect_timings(e);
-  RC(shard_check(e));
-  return check_range(e);
+  return shard_check(e);
 }
 
 int lm_fuse(lm_engine* e, const uint8_t* res_l, const uint8_t* res_r, int S, int H, int W, uint8_t* fused, int* spare_value) {
@@ -827,20 +886,22 @@ int lm_forward(lm_engine* e, int slot, const int16_t* resized, int S, uint8_t* l
   const size_t nr = (size_t)S * R * R;
   RC(e->d_resized.reserve(nr));
   RC(e->d_labels.reserve(nr));
-  CU(cudaMemcpyAsync(e->d_resized.p, resized, nr * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
-  RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, scores, nullptr));
-  CU(cudaMemcpyAsync(labels, e->d_labels.p, nr, cudaMemcpyDeviceToHost, e->st));
-  CU(cudaStreamSynchronize(e->st));
-  return check_range(e);
+  return run_checked(e, [&]() -> int {
+    CU(cudaMemcpyAsync(e->d_resized.p, resized, nr * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+    RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, scores, nullptr));
+    CU(cudaMemcpyAsync(labels, e->d_labels.p, nr, cudaMemcpyDeviceToHost, e->st));
+    return 0;
+  });
 }
 
 int lm_forward_dev(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* conv_ms) {
   if (!e || !d_resized || !d_labels) return fail(-1, "lm_forward_dev: NULL argument");
   CU(cudaSetDevice(e->device));
-  e->launches = 0;
-  RC(forward_all(e, slot, d_resized, S, d_labels, nullptr, conv_ms));
-  CU(cudaStreamSynchronize(e->st));
-  return check_range(e);
+  return run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    return forward_all(e, slot, d_resized, S, d_labels, nullptr, conv_ms);
+  });
 }
 
 int lm_postprocess(lm_engine* e, const uint8_t* labels, int S, int H, int W, const int32_t* spare, int n_spare,
@@ -918,9 +979,10 @@ int lm_debug_read_activation(lm_engine* e, int act_id, int n, float* out) {
   }
   std::vector<op_t> tmp((size_t)n * 2 * per);
   CU(cudaMemcpy(tmp.data(), e->act[act_id], tmp.size() * sizeof(op_t), cudaMemcpyDeviceToHost));
+  const float unscale = (e->range_slot >= 0 && e->range_slot < LM_MAX_SLOTS) ? 1.f / e->slots[e->range_slot].act_scale[act_id] : 1.f;
   for (int i = 0; i < n; ++i)
     for (size_t k = 0; k < per; ++k)
-      out[(size_t)i * per + k] = (float)tmp[((size_t)i * 2) * per + k] + (float)tmp[((size_t)i * 2 + 1) * per + k] * kLoUnscale;
+      out[(size_t)i * per + k] = ((float)tmp[((size_t)i * 2) * per + k] + (float)tmp[((size_t)i * 2 + 1) * per + k] * kLoUnscale) * unscale;
   return 0;
 }
 

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
                                                    const float* __restrict__ bias,   // [64]
                                                    const float* __restrict__ scale,  // [64]
                                                    const float* __restrict__ shift,  // [64]
-                                                   int N, int H, int W, int* __restrict__ range_flag) {
+                                                   int N, int H, int W, int* __restrict__ range_flag, float out_scale) {
   __shared__ float sw[64 * 9], sb[64], ss[64], sh[64];
   // (hu + 1024) / 1624 for every HU value the pre-processing can produce ([-1024, 600]): float64 division, then
   // the cast to fp32 (mask.py:168,178-182), tabulated once per block instead of nine fp64 divisions per thread
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
       float s = 0.f;
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) s = fmaf(sw[c * 9 + tap], v[tap], s);
-      yv[e] = __fadd_rn(__fmul_rn(fmaxf(s + sb[c], 0.f), ss[c]), sh[c]);
+      yv[e] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(s + sb[c], 0.f), ss[c]), sh[c]), out_scale);
     }
     op_t* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * CPT;
     split_store(yv, o, o + plane * 64, ovf);
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict_
                                                       const float* __restrict__ bias,   // [64]
                                                       const float* __restrict__ scale,  // [64]
                                                       const float* __restrict__ shift,  // [64]
-                                                      int N, int H, int W, int* __restrict__ range_flag) {
+                                                      int N, int H, int W, int* __restrict__ range_flag, float out_scale) {
   __shared__ float lut[1625];
   for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = (float)((double)i / 1624.0);
   constexpr int TPP = 64 / CPT;  // threads per pixel quad
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict_
         float s = 0.f;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) s = fmaf(wr[e][tap], win[tap / 3][px + tap % 3], s);
-        yv[e] = __fadd_rn(__fmul_rn(fmaxf(s + br[e], 0.f), sr[e]), hr[e]);
+        yv[e] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(s + br[e], 0.f), sr[e]), hr[e]), out_scale);
       }
       const size_t r = (size_t)y * W + x0 + px;
       op_t* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * CPT;
@@ -176,7 +176,7 @@ __device__ __forceinline__ float bilerp(float p00, float p01, float p10, float p
 // in: [N][h][w][C] fp32 -> out: [N][2][2h][2w][C] split planes. PyTorch semantics (align_corners=False):
 // src = max(0.5*(dst+0.5)-0.5, 0), i0 = (int)src, i1 = i0 + (i0 < size-1), l1 = src - i0, l0 = 1 - l1.
 __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict__ in, op_t* __restrict__ out,
-                                                         int N, int h, int w, int C, int* __restrict__ range_flag) {
+                                                         int N, int h, int w, int C, int* __restrict__ range_flag, float out_scale) {
   const int cq_per_pix = C / CPT;
   bool ovf = false;
   const int H = 2 * h, W = 2 * w;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const float* __restrict
       const float4 p01 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y0 * w + x1) * C) + q);
       const float4 p10 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x0) * C) + q);
       const float4 p11 = __ldg(reinterpret_cast<const float4*>(base + ((size_t)y1 * w + x1) * C) + q);
-#define LM_BILERP(f, e) vv[4 * q + e] = bilerp(p00.f, p01.f, p10.f, p11.f, lx0, lx1, ly0, ly1);
+#define LM_BILERP(f, e) vv[4 * q + e] = __fmul_rn(bilerp(p00.f, p01.f, p10.f, p11.f, lx0, lx1, ly0, ly1), out_scale);
       LM_BILERP(x, 0) LM_BILERP(y, 1) LM_BILERP(z, 2) LM_BILERP(w, 3)
 #undef LM_BILERP
     }
@@ -225,7 +225,7 @@ __device__ __forceinline__ void up_axis(int o, int n_in, int& i0, int& i1, float
   l0 = 1.f - l1;
 }
 __global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __restrict__ in, op_t* __restrict__ out,
-                                                               int N, int h, int w, int C, int* __restrict__ range_flag) {
+                                                               int N, int h, int w, int C, int* __restrict__ range_flag, float out_scale) {
   const int cq_per_pix = C / CPT;
   const int cw = w + 1, ch = h + 1;
   const int H = 2 * h, W = 2 * w;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __re
         float vv[CPT];
 #pragma unroll
         for (int e = 0; e < CPT; ++e)
-          vv[e] = bilerp(p[ry0][rx0][e], p[ry0][rx1][e], p[ry1][rx0][e], p[ry1][rx1][e], lx0, lx1, ly0, ly1);
+          vv[e] = __fmul_rn(bilerp(p[ry0][rx0][e], p[ry0][rx1][e], p[ry1][rx0][e], p[ry1][rx1][e], lx0, lx1, ly0, ly1), out_scale);
         const size_t r = (size_t)y * W + x;
         op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
         split_store(vv, o, o + oplane * C, ovf);
@@ -282,16 +282,17 @@ __global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __re
 }
 
 __global__ void prep_conv_weights_kernel(const float* __restrict__ oihw, op_t* __restrict__ out, int Cout, int Cin,
-                                         int taps, int* __restrict__ range_flag) {
+                                         int taps, int* __restrict__ range_flag, float w_scale) {
   const size_t total = (size_t)Cout * Cin * taps;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t tap = i % taps, ci = (i / taps) % Cin, co = i / ((size_t)taps * Cin);
     op_t hi, lo;
 #if LM_OPERAND_F16
-    split_f16(oihw[i], hi, lo);
-    if (!(fabsf(oihw[i]) <= kOpMax) && range_flag) *range_flag = 1;
+    const float wv = __fmul_rn(oihw[i], w_scale);   // power-of-two scale chosen by the engine so that max |w| fits fp16
+    split_f16(wv, hi, lo);
+    if (!(fabsf(wv) <= kOpMax) && range_flag) *range_flag = 1;
 #else
-    split_tf32(oihw[i], hi, lo);
+    split_tf32(__fmul_rn(oihw[i], w_scale), hi, lo);
 #endif
     const size_t o = (tap * Cout + co) * Cin + ci;
     out[o] = hi;
@@ -308,41 +309,44 @@ inline int grid_for(size_t total, int block, int num_sms) {
 }  // namespace
 
 int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
-                const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream) {
+                const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream) {
   const size_t total = (size_t)N * H * W * (64 / CPT);
-  stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag);
+  stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag, out_scale);
   return (int)cudaGetLastError();
 }
 
 int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
-                   const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream) {
+                   const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream) {
   constexpr int QW = 4;
-  if (W % QW) return launch_stem(in, out, w, bias, scale, shift, N, H, W, range_flag, num_sms, stream);
+  if (W % QW) return launch_stem(in, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, num_sms, stream);
   const size_t threads = (size_t)N * H * (W / QW) * (64 / CPT);
   size_t blocks = (threads + 127) / 128;
   const size_t cap = (size_t)num_sms * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  stem_kernel_v2<QW><<<(int)blocks, 128, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag);
+  stem_kernel_v2<QW><<<(int)blocks, 128, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag, out_scale);
   return (int)cudaGetLastError();
 }
 
-int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream) {
+int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
+                      cudaStream_t stream) {
   const size_t total = (size_t)N * 4 * h * w * (C / CPT);
-  upsample2x_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag);
+  upsample2x_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag, out_scale);
   return (int)cudaGetLastError();
 }
 
-int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream) {
+int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
+                            cudaStream_t stream) {
   const size_t total = (size_t)N * (h + 1) * (w + 1) * (C / CPT);
-  upsample2x_cells_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag);
+  upsample2x_cells_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag, out_scale);
   return (int)cudaGetLastError();
 }
 
-int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, cudaStream_t stream) {
+int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, float w_scale,
+                             cudaStream_t stream) {
   const size_t total = (size_t)Cout * Cin * taps;
   prep_conv_weights_kernel<<<(int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096), 256, 0, stream>>>(
-      oihw, static_cast<op_t*>(out), Cout, Cin, taps, range_flag);
+      oihw, static_cast<op_t*>(out), Cout, Cin, taps, range_flag, w_scale);
   return (int)cudaGetLastError();
 }
 

@@ -8,14 +8,18 @@ namespace lm {
 // resized HU slices int16 [N][H][W] -> split planes [N][2][H][W][64]
 // (range_flag: device int set to 1 when a value leaves the operand format's range; may be nullptr)
 int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
-                const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream);
+                const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream);
 // same result from a different work assignment (weights in registers, 4-pixel quads); opt-in, see forward_misc.cu
 int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
-                   const float* shift, int N, int H, int W, int* range_flag, int num_sms, cudaStream_t stream);
+                   const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream);
 // fp32 [N][h][w][C] -> split planes [N][2][2h][2w][C]
-int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream);
+// (all planes are stored as value * out_scale, a power of two chosen by the engine: conv_tc.cuh ConvParams)
+int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
+                      cudaStream_t stream);
 // same samples, one thread per cell between four input pixels (1 load per output instead of 4); see forward_misc.cu
-int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, int num_sms, cudaStream_t stream);
+int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
+                            cudaStream_t stream);
 // OIHW fp32 -> [2][taps][Cout][Cin] hi/lo operand planes
-int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, cudaStream_t stream);
+int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, float w_scale,
+                             cudaStream_t stream);
 }  // namespace lm

@@ -145,6 +145,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   p.N = N; p.H = L.H; p.W = L.W; p.C0 = L.C0; p.C1 = L.C1; p.Cout = L.Cout; p.taps = L.taps; p.mode = L.mode;
   p.chunk_kb = chunk_kb; p.dual_issue = g_dual; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
   p.head_w = b.hw; p.head_b = b.hb; p.K = L.K; p.labels = b.labels; p.scores = b.scores; p.range_flag = b.range_flag;
+  p.in_unscale = 1.f; p.out_scale = 1.f;
   ConvMaps maps;
   int r = make_conv_maps(&maps, b.src0, b.src1, b.w, p, N);
   if (r) { printf("make_conv_maps failed %d\n", r); exit(2); }
