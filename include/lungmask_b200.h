@@ -84,6 +84,15 @@ LM_API int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const 
 LM_API int lm_fuse(lm_engine* e, const uint8_t* res_l, const uint8_t* res_r, int S, int H, int W, uint8_t* fused,
                    int* spare_value);
 
+/* LMInferer.apply for a SimpleITK image, mask.py:157-164,204-208,223-232: the array `vol` (n0,n1,n2) is in the image's
+ * NATIVE orientation; lps = transpose(vol, perm) flipped along every axis k with flip[k] != 0 is the array of the image
+ * re-oriented to DICOM "LPS" (lungmask_b200/orient.py derives perm / flip from the direction cosines).  The engine
+ * re-orients on the device, runs the path on the LPS array and returns the mask in the native orientation (n0,n1,n2).
+ * slot_fill >= 0 selects the fusion of mask.py:223-232, whose spare-label fusion and post-processing run on the
+ * native-orientation results exactly as in the reference (each _inference call re-orients its own result back). */
+LM_API int lm_apply_volume_oriented(lm_engine* e, int slot, int slot_fill, const int16_t* vol, int n0, int n1, int n2,
+                                    const int* perm, const int* flip, int flags, uint8_t* out);
+
 /* ---- one volume over several GPUs (the reference is single-device, mask.py:118-121) ----------------
  * One process and one engine per GPU.  Slices are independent up to the 3-D post-processing (utils.py:48-51,
  * mask.py:173-187,196-202 vs utils.py:293-358): rank r of `world` runs pre-processing and the network on the contiguous

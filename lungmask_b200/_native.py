@@ -40,6 +40,7 @@ def lib():
         "lm_apply_volume_dev": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_fused": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_fused_dev": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
+        "lm_apply_volume_oriented": ([vp, i32, i32, i16p, i32, i32, i32, vp, vp, i32, u8p], i32),
         "lm_shard_init": ([vp, i32, i32, i32], i32),
         "lm_shard_handle_bytes": ([], C.c_size_t),
         "lm_shard_export": ([vp, vp], i32),
@@ -69,7 +70,7 @@ def lib():
 
 
 EXPORTS = ["lm_create", "lm_destroy", "lm_last_error", "lm_device", "lm_batch_capacity", "lm_weight_blob_floats",
-           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_apply_fused_dev", "lm_fuse", "lm_preprocess",
+           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_apply_fused_dev", "lm_apply_volume_oriented", "lm_fuse", "lm_preprocess",
            "lm_shard_init", "lm_shard_handle_bytes", "lm_shard_export", "lm_shard_connect", "lm_shard_labels",
            "lm_apply_volume_sharded", "lm_apply_volume_sharded_dev",
            "lm_simple_bodymask", "lm_forward", "lm_forward_dev", "lm_postprocess", "lm_reshape_masks",
@@ -163,6 +164,17 @@ class Engine:
         S, H, W = shape
         _check(lib().lm_apply_fused_dev(self._h, slot_base, slot_fill, C.c_void_p(d_vol_ptr), S, H, W,
                                         0 if postprocess else FLAG_NO_POSTPROCESS, C.c_void_p(d_out_ptr)))
+
+    def apply_volume_oriented(self, slot, vol, perm, flip, slot_fill=-1, postprocess=True):
+        """`vol` in its native orientation; (perm, flip) = lungmask_b200.orient.array_transform_to_lps(code)."""
+        vol = _as(vol, np.int16, 3)
+        out = np.empty(vol.shape, np.uint8)
+        pa = (C.c_int * 3)(*[int(x) for x in perm])
+        fa = (C.c_int * 3)(*[1 if x else 0 for x in flip])
+        n0, n1, n2 = vol.shape
+        _check(lib().lm_apply_volume_oriented(self._h, slot, int(slot_fill), _ptr(vol), n0, n1, n2, pa, fa,
+                                              0 if postprocess else FLAG_NO_POSTPROCESS, _ptr(out)))
+        return out
 
     # ---- one volume over several GPUs (one engine per rank; see include/lungmask_b200.h)
     def shard_init(self, rank, world, max_slices):

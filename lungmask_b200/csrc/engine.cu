@@ -84,6 +84,8 @@ const ActSpec ACT[NUM_ACT] = {
     {4, 512, 0}, {3, 512, 1}, {3, 512, 1}, {3, 512, 1}, {3, 256, 0}, {2, 256, 1}, {2, 256, 1}, {2, 256, 1},
     {2, 128, 0}, {1, 128, 1}, {1, 128, 1}, {1, 128, 1}, {1, 64, 0}, {0, 64, 1}, {0, 64, 1}};
 
+constexpr int RANGE_STRIDE = NUM_ACT + 1;  // range flags per weight slot: one per activation tensor + one for the weights
+
 // The 21 tensor-core convolutions (the stem 1->64 runs on CUDA cores). Order = execution order = blob order
 // for the 3x3 layers (the four 1x1 "up" layers come after them in the blob, see lungmask_b200.h).
 const LayerSpec LAYERS[] = {
@@ -159,13 +161,14 @@ struct lm_engine {
   uint32_t shard_epoch = 0;
   uint32_t* h_shard_err = nullptr;  // pinned copy of the block's error word
   int32_t* d_spare = nullptr;  // device int32[16]: spare label values computed on the device (fusion, mask.py:228)
-  int* d_range = nullptr;   // device flags [NUM_ACT + 1]: a value of activation tensor a (or, last entry, a weight) left the
-                            // operand format's range (fp16 build: |x * scale| > 65504)
+  int* d_range = nullptr;   // device flags [LM_MAX_SLOTS][NUM_ACT + 1]: a value of activation tensor a (or, last entry, a
+                            // weight) of that slot's network left the operand format's range (fp16 build: |x * scale| > 65504)
   int* h_range = nullptr;   // pinned host copy, refreshed at the end of every forward
-  int range_slot = -1;      // the slot whose forward the flags belong to
+  int range_slot = -1;      // the slot of the last forward (lm_debug_read_activation unscales with its scales)
   int range_retries = 0;
   Slot slots[LM_MAX_SLOTS];
-  DevBuf<int16_t> d_vol, d_resized;
+  DevBuf<int16_t> d_vol, d_resized, d_native;
+  DevBuf<uint8_t> d_lps_out, d_native_l, d_native_r;
   DevBuf<int32_t> d_boxes;
   DevBuf<uint8_t> d_labels, d_post, d_out, d_out2, d_fused, d_mask;
   DevBuf<float> d_scores;
@@ -230,8 +233,9 @@ int upload(float** dst, const float* src, size_t n, cudaStream_t st) {
 
 int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_t* d_labels, float* d_scores,
                   bool time_convs) {
+  int* const range = e->d_range + (size_t)(&s - e->slots) * RANGE_STRIDE;
   RC((e->stem_v2 ? launch_stem_v2 : launch_stem)(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
-                                                 e->d_range + A0, s.act_scale[A0], e->num_sms, e->st));
+                                                 range + A0, s.act_scale[A0], e->num_sms, e->st));
   e->launches++;
   int up = 0;
   for (int i = 0; i < NUM_LAYERS; ++i) {
@@ -239,7 +243,7 @@ int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_
     p.N = n;
     p.chunk_kb = (p.Cout >= 128) ? e->chunk_kb_wide : e->chunk_kb;
     const LayerSpec& L = LAYERS[i];
-    p.range_flag = L.dst >= 0 ? e->d_range + L.dst : nullptr;
+    p.range_flag = L.dst >= 0 ? range + L.dst : nullptr;
     p.in_unscale = 1.f / (s.act_scale[L.src0] * s.lw[i].w_scale);   // src1 (virtual concat) shares src0's scale group
     p.out_scale = (L.mode == kModeReluBn || L.mode == kModeReluBnPool) ? s.act_scale[L.dst] : 1.f;
     p.dual_issue = e->dual_issue;
@@ -256,7 +260,7 @@ int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_
     if (up < 4 && UPS[up].after_layer == i) {
       const ActSpec& src = ACT[UPS[up].src];
       RC((e->upsample_v2 ? launch_upsample2x_cells : launch_upsample2x)(static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n,
-                                                                      R >> src.level, R >> src.level, src.C, e->d_range + UPS[up].dst,
+                                                                      R >> src.level, R >> src.level, src.C, range + UPS[up].dst,
                                                                       s.act_scale[UPS[up].dst], e->num_sms, e->st));
       e->launches++;
       ++up;
@@ -297,7 +301,7 @@ int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t
       CU(cudaStreamSynchronize(e->st));
     }
   }
-  CU(cudaMemcpyAsync(e->h_range, e->d_range, (NUM_ACT + 1) * sizeof(int), cudaMemcpyDeviceToHost, e->st));  // read by range_finish after the caller's sync
+  CU(cudaMemcpyAsync(e->h_range, e->d_range, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, e->st));  // read by range_finish after the caller's sync
   e->range_slot = slot;
   if (conv_ms) {  // device time of the tensor-core convolution launches alone (CUDA events on the launch stream)
     CU(cudaStreamSynchronize(e->st));
@@ -339,26 +343,30 @@ int inference_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, in
 // Returns 0 (no), 1 (yes: the offending tensors' power-of-two scales were lowered - run the forward again) or an error.
 int range_finish(lm_engine* e) {
   bool any = false;
-  for (int a = 0; a <= NUM_ACT; ++a) any |= e->h_range[a] != 0;
+  for (int i = 0; i < LM_MAX_SLOTS * RANGE_STRIDE; ++i) any |= e->h_range[i] != 0;
   if (!any) { e->range_retries = 0; return 0; }
-  cudaMemsetAsync(e->d_range, 0, (NUM_ACT + 1) * sizeof(int), e->st);
-  const bool weight_flag = e->h_range[NUM_ACT] != 0;
-  bool flagged[NUM_ACT] = {};
-  for (int a = 0; a < NUM_ACT; ++a) { flagged[a] = e->h_range[a] != 0; e->h_range[a] = 0; }
-  e->h_range[NUM_ACT] = 0;
-  if (weight_flag || e->range_slot < 0 || e->range_slot >= LM_MAX_SLOTS || ++e->range_retries > 4) {
+  cudaMemsetAsync(e->d_range, 0, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int), e->st);
+  const bool give_up = ++e->range_retries > 4;
+  bool weight_flag = false;
+  for (int sl = 0; sl < LM_MAX_SLOTS; ++sl) {
+    int* h = e->h_range + sl * RANGE_STRIDE;
+    Slot& s = e->slots[sl];
+    weight_flag |= h[NUM_ACT] != 0;
+    h[NUM_ACT] = 0;
+    for (int a = 0; a < NUM_ACT; ++a) {
+      if (!h[a]) continue;
+      const int g = scale_group(a);
+      for (int b = 0; b < NUM_ACT; ++b) {   // one step per group and re-run, whichever members raised their flags
+        if (scale_group(b) != g) continue;
+        if (!give_up && s.act_scale[b] > 1e-30f) s.act_scale[b] *= (1.f / 256.f);
+        h[b] = 0;
+      }
+    }
+  }
+  if (weight_flag || give_up) {
     e->range_retries = 0;
     return fail(LM_ERR_RANGE, "an activation exceeded the fp16 operand range even after rescaling by 2^-32 (|x| > 2.8e14): "
                               "the weights are not a usable network (rebuild with -DLM_OPERAND_F16=0 for tf32 operands)");
-  }
-  Slot& s = e->slots[e->range_slot];
-  for (int a = 0; a < NUM_ACT; ++a) {
-    if (!flagged[a]) continue;
-    const int g = scale_group(a);
-    for (int b = 0; b < NUM_ACT; ++b)
-      if (scale_group(b) == g && s.act_scale[b] > 1e-30f) s.act_scale[b] *= (1.f / 256.f);
-    for (int b = 0; b < NUM_ACT; ++b)   // one step per group and retry, whichever member raised the flag
-      if (scale_group(b) == g) flagged[b] = false;
   }
   return 1;
 }
@@ -506,10 +514,10 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
     CU(cudaMalloc(&e->act[a], ACT[a].split ? elems * 2 * sizeof(op_t) : elems * sizeof(float)));
   }
   CU(cudaMalloc(&e->d_spare, 16 * sizeof(int32_t)));
-  CU(cudaMalloc(&e->d_range, (NUM_ACT + 1) * sizeof(int)));
-  CU(cudaMemset(e->d_range, 0, (NUM_ACT + 1) * sizeof(int)));
-  CU(cudaMallocHost(&e->h_range, (NUM_ACT + 1) * sizeof(int)));
-  memset(e->h_range, 0, (NUM_ACT + 1) * sizeof(int));
+  CU(cudaMalloc(&e->d_range, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int)));
+  CU(cudaMemset(e->d_range, 0, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int)));
+  CU(cudaMallocHost(&e->h_range, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int)));
+  memset(e->h_range, 0, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int));
   RC(e->d_scratch.reserve(64));
   *out = e;
   return 0;
@@ -528,6 +536,7 @@ void lm_destroy(lm_engine* e) {
     cudaFree(s.stem_w); cudaFree(s.stem_bias); cudaFree(s.stem_scale); cudaFree(s.stem_shift); cudaFree(s.head_w); cudaFree(s.head_b);
     for (auto& l : s.lw) { cudaFree(l.w); cudaFree(l.bias); cudaFree(l.scale); cudaFree(l.shift); }
   }
+  e->d_native.release(); e->d_lps_out.release(); e->d_native_l.release(); e->d_native_r.release();
   e->d_vol.release(); e->d_resized.release(); e->d_boxes.release(); e->d_labels.release(); e->d_post.release();
   e->d_out.release(); e->d_out2.release(); e->d_fused.release(); e->d_mask.release(); e->d_scores.release(); e->d_scratch.release();
   e->post.release();
@@ -582,7 +591,7 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
     s.lw[i].w_scale = ws;
     CU(cudaMemcpyAsync(d_tmp, q, nw * sizeof(float), cudaMemcpyHostToDevice, e->st)); q += nw;
     if (!s.lw[i].w) CU(cudaMalloc(&s.lw[i].w, 2 * nw * sizeof(op_t)));
-    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->d_range + NUM_ACT, ws, e->st));
+    RC(launch_prep_conv_weights(d_tmp, s.lw[i].w, L.Cout, Cin, L.taps, e->d_range + slot * RANGE_STRIDE + NUM_ACT, ws, e->st));
     CU(cudaStreamSynchronize(e->st));
     RC(upload(&s.lw[i].bias, q, L.Cout, e->st)); q += L.Cout;
     if (has_bn) {
@@ -601,11 +610,12 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   RC(upload(&s.head_w, q, (size_t)K * 64, e->st)); q += (size_t)K * 64;
   RC(upload(&s.head_b, q, K, e->st)); q += K;
   if ((size_t)(q - blob) != n_floats) return fail(-1, "lm_load_weights: internal blob walk mismatch");
-  CU(cudaMemcpyAsync(e->h_range + NUM_ACT, e->d_range + NUM_ACT, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+  int* const h_wflag = e->h_range + slot * RANGE_STRIDE + NUM_ACT;
+  CU(cudaMemcpyAsync(h_wflag, e->d_range + slot * RANGE_STRIDE + NUM_ACT, sizeof(int), cudaMemcpyDeviceToHost, e->st));
   CU(cudaStreamSynchronize(e->st));
-  if (e->h_range[NUM_ACT]) {
-    e->h_range[NUM_ACT] = 0;
-    CU(cudaMemsetAsync(e->d_range + NUM_ACT, 0, sizeof(int), e->st));
+  if (*h_wflag) {
+    *h_wflag = 0;
+    CU(cudaMemsetAsync(e->d_range + slot * RANGE_STRIDE + NUM_ACT, 0, sizeof(int), e->st));
     return fail(LM_ERR_RANGE, "lm_load_weights: a scaled convolution weight still exceeds the fp16 operand range (internal error)");
   }
   for (float& sc : s.act_scale) sc = 1.f;   // new weights: activation ranges are unknown again
@@ -716,6 +726,54 @@ int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const int16_t
     e->ev_used = 0;
     CU(cudaEventRecord(e->ev[0], e->st));
     RC(fused_enqueue(e, slot_base, slot_fill, d_vol, S, H, W, flags, d_out));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
+  collect_timings(e);
+  return 0;
+}
+
+int lm_apply_volume_oriented(lm_engine* e, int slot, int slot_fill, const int16_t* vol, int n0, int n1, int n2, const int* perm,
+                             const int* flip, int flags, uint8_t* out) {
+  if (!e || !vol || !out || !perm || !flip) return fail(-1, "lm_apply_volume_oriented: NULL argument");
+  if (n0 < 1 || n1 < 1 || n2 < 1) return fail(-1, "lm_apply_volume_oriented: empty volume");
+  int seen = 0;
+  for (int k = 0; k < 3; ++k) { if (perm[k] < 0 || perm[k] > 2) return fail(-1, "lm_apply_volume_oriented: perm is not a permutation"); seen |= 1 << perm[k]; }
+  if (seen != 7) return fail(-1, "lm_apply_volume_oriented: perm is not a permutation");
+  if (slot < 0 || slot >= LM_MAX_SLOTS || !e->slots[slot].loaded) return fail(-30, "weight slot %d not loaded", slot);
+  const bool fused = slot_fill >= 0;
+  if (fused && (slot_fill >= LM_MAX_SLOTS || !e->slots[slot_fill].loaded)) return fail(-30, "weight slot %d not loaded", slot_fill);
+  CU(cudaSetDevice(e->device));
+  const int dn[3] = {n0, n1, n2};
+  const int dl[3] = {dn[perm[0]], dn[perm[1]], dn[perm[2]]};   // the LPS array: (slices, rows, columns) of the path
+  const int fl[3] = {flip[0] != 0, flip[1] != 0, flip[2] != 0};
+  const size_t n = (size_t)n0 * n1 * n2;
+  RC(e->d_native.reserve(n));
+  RC(e->d_vol.reserve(n));
+  RC(e->d_lps_out.reserve(n));
+  RC(e->d_native_l.reserve(n));
+  if (fused) { RC(e->d_native_r.reserve(n)); RC(e->d_fused.reserve(n)); }
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    CU(cudaMemcpyAsync(e->d_native.p, vol, n * sizeof(int16_t), cudaMemcpyHostToDevice, e->st));
+    RC(launch_orient_i16(e->d_native.p, e->d_vol.p, dl, perm, fl, 1, e->num_sms, e->st));            // sitk.DICOMOrient(image, "LPS"), mask.py:163
+    const int inner = fused ? (flags & LM_FLAG_NO_POSTPROCESS) : flags;
+    RC(inference_dev(e, slot, e->d_vol.p, dl[0], dl[1], dl[2], inner, e->d_lps_out.p));
+    RC(launch_orient_u8(e->d_lps_out.p, e->d_native_l.p, dl, perm, fl, 0, e->num_sms, e->st));       // back, mask.py:204-208
+    e->launches += 2;
+    const uint8_t* result = e->d_native_l.p;
+    if (fused) {   // the fusion and its post-processing work on the NATIVE-orientation results (mask.py:225-232)
+      RC(inference_dev(e, slot_fill, e->d_vol.p, dl[0], dl[1], dl[2], inner, e->d_lps_out.p));
+      RC(launch_orient_u8(e->d_lps_out.p, e->d_native_r.p, dl, perm, fl, 0, e->num_sms, e->st));
+      RC(fuse_device(e->d_native_l.p, e->d_native_r.p, n, e->d_scratch.p, e->d_spare, e->num_sms, e->st));
+      e->launches += 4;
+      RC(postprocess_device(e->post, e->d_native_l.p, n0, n1, n2, nullptr, 0, e->d_spare, 1, 3, e->slots[slot].K, e->d_fused.p,
+                            e->num_sms, e->st, &e->launches));
+      result = e->d_fused.p;
+    }
+    CU(cudaMemcpyAsync(out, result, n, cudaMemcpyDeviceToHost, e->st));
     CU(cudaEventRecord(e->ev[6], e->st));
     return 0;
   }));

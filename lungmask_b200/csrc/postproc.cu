@@ -277,7 +277,7 @@ constexpr int MAX_SPARE = 16;
 struct SpareArgs { int n; int v[MAX_SPARE]; const int32_t* d_extra; int n_extra; };
 
 // spare tables + record / present / best reset (one block)
-__global__ void post_setup_kernel(uint32_t* __restrict__ small, SpareArgs sp, int clear_sticky) {
+__global__ void post_setup_kernel(uint32_t* small, SpareArgs sp, int clear_sticky) {
   uint8_t* spare_value = reinterpret_cast<uint8_t*>(small) + B_SPARE_VALUE;
   int32_t* spare_list = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(small) + B_SPARE_LIST);
   unsigned long long* best = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(small) + B_BEST);
@@ -303,7 +303,7 @@ __global__ void post_setup_kernel(uint32_t* __restrict__ small, SpareArgs sp, in
 }
 
 // region tables for ids 0..min(R, cap): zero / identity, spare_id[i] = "the ID i equals a spare entry" (utils.py:322)
-__global__ void region_init_kernel(uint32_t* __restrict__ small, uint32_t cap, uint32_t* __restrict__ area,
+__global__ void region_init_kernel(uint32_t* small, uint32_t cap, uint32_t* __restrict__ area,
                                    uint32_t* __restrict__ count, uint8_t* __restrict__ value, int* __restrict__ bbox,
                                    uint32_t* __restrict__ cur, uint8_t* __restrict__ to_label, uint8_t* __restrict__ spare_id) {
   const uint32_t R = small[W_R];
@@ -594,7 +594,7 @@ __global__ void first_present_kernel(uint32_t* __restrict__ small) {
   }
 }
 // opens the finalisation of label `v`: gate = present and not the first value; resets the extent
-__global__ void label_begin_kernel(uint32_t* __restrict__ small, int v) {
+__global__ void label_begin_kernel(uint32_t* small, int v) {
   if (threadIdx.x == 0) {
     small[W_GATE] = (small[W_PRESENT + v] && small[W_FIRST] != (uint32_t)v) ? 1u : 0u;
     int* bb = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(small) + B_BBOX1);

@@ -309,7 +309,60 @@ resize_kernel(const int16_t* __restrict__ vol, int S, int H, int W, const int32_
   }
 }
 
+// Axis permutation + flips between an array in its native orientation and the LPS array the path works on
+// (sitk.DICOMOrient, mask.py:157-164,204-208; lungmask_b200/orient.py states the index map):
+//   lps[i0][i1][i2] = native[c],  c[perm[k]] = flip[k] ? dims_lps[k] - 1 - i_k : i_k.
+// to_lps != 0: threads walk the LPS array (coalesced writes) and gather; to_lps == 0: threads walk the native array
+// (coalesced writes) and gather from the LPS array - the inverse map.
+struct OrientMap { int dl[3]; int perm[3]; int flip[3]; };
+template <typename T>
+__global__ void __launch_bounds__(256) orient_kernel(const T* __restrict__ src, T* __restrict__ dst, OrientMap m, int to_lps) {
+  int dn[3];  // native dims: dn[perm[k]] = dl[k]
+  for (int k = 0; k < 3; ++k) dn[m.perm[k]] = m.dl[k];
+  const size_t n = (size_t)m.dl[0] * m.dl[1] * m.dl[2];
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    if (to_lps) {
+      int i[3];
+      i[2] = (int)(t % m.dl[2]);
+      i[1] = (int)((t / m.dl[2]) % m.dl[1]);
+      i[0] = (int)(t / ((size_t)m.dl[2] * m.dl[1]));
+      int c[3];
+      for (int k = 0; k < 3; ++k) c[m.perm[k]] = m.flip[k] ? m.dl[k] - 1 - i[k] : i[k];
+      dst[t] = src[((size_t)c[0] * dn[1] + c[1]) * dn[2] + c[2]];
+    } else {
+      int c[3];
+      c[2] = (int)(t % dn[2]);
+      c[1] = (int)((t / dn[2]) % dn[1]);
+      c[0] = (int)(t / ((size_t)dn[2] * dn[1]));
+      int i[3];
+      for (int k = 0; k < 3; ++k) i[k] = m.flip[k] ? m.dl[k] - 1 - c[m.perm[k]] : c[m.perm[k]];
+      dst[t] = src[((size_t)i[0] * m.dl[1] + i[1]) * m.dl[2] + i[2]];
+    }
+  }
+}
+
 }  // namespace
+
+template <typename T>
+static int launch_orient_t(const T* src, T* dst, const int dims_lps[3], const int perm[3], const int flip[3], int to_lps, int num_sms,
+                           cudaStream_t stream) {
+  OrientMap m;
+  for (int k = 0; k < 3; ++k) { m.dl[k] = dims_lps[k]; m.perm[k] = perm[k]; m.flip[k] = flip[k]; }
+  const size_t n = (size_t)dims_lps[0] * dims_lps[1] * dims_lps[2];
+  size_t g = (n + 255) / 256;
+  if (g > (size_t)num_sms * 16) g = (size_t)num_sms * 16;
+  if (g < 1) g = 1;
+  orient_kernel<T><<<(int)g, 256, 0, stream>>>(src, dst, m, to_lps);
+  return (int)cudaGetLastError();
+}
+int launch_orient_i16(const int16_t* src, int16_t* dst, const int dims_lps[3], const int perm[3], const int flip[3], int to_lps,
+                      int num_sms, cudaStream_t stream) {
+  return launch_orient_t<int16_t>(src, dst, dims_lps, perm, flip, to_lps, num_sms, stream);
+}
+int launch_orient_u8(const uint8_t* src, uint8_t* dst, const int dims_lps[3], const int perm[3], const int flip[3], int to_lps,
+                     int num_sms, cudaStream_t stream) {
+  return launch_orient_t<uint8_t>(src, dst, dims_lps, perm, flip, to_lps, num_sms, stream);
+}
 
 int preproc_smem_bytes() { return (int)sizeof(Smem); }
 

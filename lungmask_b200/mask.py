@@ -11,7 +11,7 @@ from typing import Optional, Union
 
 import numpy as np
 
-from . import _native
+from . import _native, orient
 from .logger import logger
 
 # model name -> (release URL, number of classes); lungmask/mask.py:22-35
@@ -153,23 +153,36 @@ class LMInferer:
             self.fillmodelm = get_model(self.fillmodel, fillmodel_path)
             self.engine.load_weights(1, self.fillmodelm.blob, self.fillmodelm.n_classes)
 
-    # -- SimpleITK inputs are oriented to LPS first and back afterwards (mask.py:157-164,204-208)
+    # -- SimpleITK inputs are oriented to LPS first and back afterwards (mask.py:157-164,204-208): here that is an
+    #    axis permutation + flips done by the engine on the device (lungmask_b200/orient.py, lm_apply_volume_oriented)
     @staticmethod
     def _sitk():
         try:
             import SimpleITK as sitk
-            return sitk if hasattr(sitk, "DICOMOrient") else None
+            return sitk
         except Exception:
             return None
 
-    def _run(self, volume: np.ndarray) -> np.ndarray:
+    def _run(self, volume: np.ndarray, code: str = "LPS") -> np.ndarray:
         vol = _to_int16_volume(volume)
-        if self.fillmodel is None:
-            return self.engine.apply_volume(0, vol, postprocess=self.volume_postprocessing)
-        logger.info(f"Apply: {self.modelname}")
-        logger.info(f"Apply: {self.fillmodel}")
-        logger.info("Fusing results... this may take up to several minutes!")
-        return self.engine.apply_fused(0, 1, vol, postprocess=self.volume_postprocessing)
+        fused = self.fillmodel is not None
+        if fused:
+            logger.info(f"Apply: {self.modelname}")
+            logger.info(f"Apply: {self.fillmodel}")
+            logger.info("Fusing results... this may take up to several minutes!")
+        if code == "LPS":
+            if not fused:
+                return self.engine.apply_volume(0, vol, postprocess=self.volume_postprocessing)
+            return self.engine.apply_fused(0, 1, vol, postprocess=self.volume_postprocessing)
+        perm, flip = orient.array_transform_to_lps(code)
+        return self.engine.apply_volume_oriented(0, vol, perm, flip, slot_fill=1 if fused else -1,
+                                                 postprocess=self.volume_postprocessing)
+
+    def apply_oriented(self, array: np.ndarray, direction) -> np.ndarray:
+        """What `apply(sitk_image)` does, for callers without SimpleITK: `array` = sitk.GetArrayFromImage(image)
+        (axes z, y, x), `direction` = image.GetDirection() (9 direction cosines).  The mask comes back in the array's
+        own orientation (mask.py:157-164,204-208)."""
+        return self._run(array, orient.orientation_from_direction(direction))
 
     def apply(self, image) -> np.ndarray:
         """Segments a volume: numpy (slices, H, W) or sitk.Image -> uint8 labels of the same shape
@@ -179,13 +192,7 @@ class LMInferer:
         sitk = self._sitk()
         if sitk is None or not isinstance(image, sitk.Image):
             raise TypeError("apply() expects a numpy array or a SimpleITK image")
-        orient = sitk.DICOMOrientImageFilter_GetOrientationFromDirectionCosines(image.GetDirection())
-        if orient != "LPS":
-            image = sitk.DICOMOrient(image, "LPS")
-        out = self._run(sitk.GetArrayFromImage(image))
-        if orient != "LPS":
-            out = sitk.GetArrayFromImage(sitk.DICOMOrient(sitk.GetImageFromArray(out), orient))
-        return out.astype(np.uint8)
+        return self.apply_oriented(sitk.GetArrayFromImage(image), image.GetDirection())
 
 
 def apply(image, model=None, force_cpu=False, batch_size=20, volume_postprocessing=True, tqdm_disable=False):

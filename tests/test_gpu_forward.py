@@ -181,3 +181,26 @@ def test_sharded_path_equals_whole_volume(engine, models):
     engine.load_weights(0, m.blob, m.n_classes)
     vol = synth.phantom(5, 180, 200, seed=12)
     assert np.array_equal(apply_sharded(engine, 0, vol, 0, 1), engine.apply_volume(0, vol))
+
+
+@pytest.mark.parametrize("code", ["RAS", "PLI", "SAL"])
+def test_orientation_on_device(engine, models, code, tmp_path):
+    """f2: lm_apply_volume_oriented == re-orient with numpy, run the LPS path, orient back (mask.py:157-164,204-208),
+    single model and fusion (whose post-processing runs in the NATIVE orientation, mask.py:225-232)."""
+    from lungmask_b200 import orient
+    m6, m3 = _blob(models[6]), _blob(models[3])
+    engine.load_weights(0, m6.blob, m6.n_classes)
+    engine.load_weights(1, m3.blob, m3.n_classes)
+    lps = synth.phantom(5, 120, 136, seed=17)
+    native = orient.from_lps(lps, code)
+    perm, flip = orient.array_transform_to_lps(code)
+    assert np.array_equal(orient.to_lps(native, code), lps)
+    got = engine.apply_volume_oriented(1, native, perm, flip)
+    assert got.shape == native.shape
+    assert np.array_equal(got, orient.from_lps(engine.apply_volume(1, lps), code))
+    res_l = orient.from_lps(engine.apply_volume(0, lps), code)
+    res_r = orient.from_lps(engine.apply_volume(1, lps), code)
+    pre, spare = engine.fuse(res_l, res_r)
+    want_fused = engine.postprocess(pre, spare=[spare])             # native-orientation fusion, stage by stage
+    assert np.array_equal(engine.apply_volume_oriented(0, native, perm, flip, slot_fill=1), want_fused)
+    assert np.array_equal(want_fused, restate.fuse(res_l, res_r))
