@@ -40,6 +40,8 @@ def lib():
         "lm_apply_volume_dev": ([vp, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_fused": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
         "lm_apply_fused_dev": ([vp, i32, i32, i16p, i32, i32, i32, i32, u8p], i32),
+        "lm_apply_volume_float": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, u8p], i32),
+        "lm_preprocess_float": ([vp, vp, i32, i32, i32, i32, f32p, i32p], i32),
         "lm_apply_volume_oriented": ([vp, i32, i32, i16p, i32, i32, i32, vp, vp, i32, u8p], i32),
         "lm_shard_init": ([vp, i32, i32, i32], i32),
         "lm_shard_handle_bytes": ([], C.c_size_t),
@@ -70,7 +72,7 @@ def lib():
 
 
 EXPORTS = ["lm_create", "lm_destroy", "lm_last_error", "lm_device", "lm_batch_capacity", "lm_weight_blob_floats",
-           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_apply_fused_dev", "lm_apply_volume_oriented", "lm_fuse", "lm_preprocess",
+           "lm_load_weights", "lm_apply_volume", "lm_apply_volume_dev", "lm_apply_fused", "lm_apply_fused_dev", "lm_apply_volume_oriented", "lm_apply_volume_float", "lm_preprocess_float", "lm_fuse", "lm_preprocess",
            "lm_shard_init", "lm_shard_handle_bytes", "lm_shard_export", "lm_shard_connect", "lm_shard_labels",
            "lm_apply_volume_sharded", "lm_apply_volume_sharded_dev",
            "lm_simple_bodymask", "lm_forward", "lm_forward_dev", "lm_postprocess", "lm_reshape_masks",
@@ -164,6 +166,29 @@ class Engine:
         S, H, W = shape
         _check(lib().lm_apply_fused_dev(self._h, slot_base, slot_fill, C.c_void_p(d_vol_ptr), S, H, W,
                                         0 if postprocess else FLAG_NO_POSTPROCESS, C.c_void_p(d_out_ptr)))
+
+    def apply_volume_float(self, slot, vol, slot_fill=-1, postprocess=True):
+        """float32 / float64 HU volume (the dtype is kept through pre-processing and normalisation, as the reference does)."""
+        vol = np.asarray(vol)
+        if vol.dtype not in (np.float32, np.float64):
+            raise TypeError("apply_volume_float expects float32 or float64, got %s" % vol.dtype)
+        vol = _as(vol, vol.dtype, 3)
+        out = np.empty(vol.shape, np.uint8)
+        S, H, W = vol.shape
+        _check(lib().lm_apply_volume_float(self._h, slot, int(slot_fill), _ptr(vol), 1 if vol.dtype == np.float64 else 0, S, H, W,
+                                           0 if postprocess else FLAG_NO_POSTPROCESS, _ptr(out)))
+        return out
+
+    def preprocess_float(self, vol):
+        vol = np.asarray(vol)
+        if vol.dtype not in (np.float32, np.float64):
+            raise TypeError("preprocess_float expects float32 or float64, got %s" % vol.dtype)
+        vol = _as(vol, vol.dtype, 3)
+        S, H, W = vol.shape
+        norm = np.empty((S, NET_RES, NET_RES), np.float32)
+        boxes = np.empty((S, 4), np.int32)
+        _check(lib().lm_preprocess_float(self._h, _ptr(vol), 1 if vol.dtype == np.float64 else 0, S, H, W, _ptr(norm), _ptr(boxes)))
+        return norm, boxes
 
     def apply_volume_oriented(self, slot, vol, perm, flip, slot_fill=-1, postprocess=True):
         """`vol` in its native orientation; (perm, flip) = lungmask_b200.orient.array_transform_to_lps(code)."""

@@ -35,6 +35,7 @@
 //   * persistent CTAs (one per SM), warp-specialised: warp 0 TMA producer, warp 1 (and optionally 3) MMA issuer
 //     - one elected lane running mma_issue_loop -, warp 2 TMEM allocator, warps 4-11 epilogue (TMEM lane quarter
 //     = warp % 4, two warps share a quarter and split the columns or, for BN = 64, take alternate tiles).
+#include <atomic>
 #include <stdio.h>
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
@@ -425,14 +426,14 @@ int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const voi
 template <int BN>
 static int launch_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
-  static unsigned long long attr_set_mask = 0ull;
+  static std::atomic<unsigned long long> attr_set_mask{0ull};  // engines of several host threads may launch concurrently
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
-  if (!((attr_set_mask >> dev) & 1ull)) {
+  if (!((attr_set_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BN>::DYN_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set_mask |= 1ull << dev;
+    attr_set_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
   const int total = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN);
   const int grid = total < num_sms ? total : num_sms;

@@ -28,6 +28,7 @@
 //     count 2 x epilogue warps (the peer's epilogue warps arrive remotely).
 //   * TMEM is allocated with cta_group::2 by warp 2 of both CTAs; cluster barriers bracket the kernel body.
 //   * one MMA issuer (the leader's warp 1); grid = pairs * 2, cluster dimension 2.
+#include <atomic>
 #include <stdio.h>
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
@@ -260,14 +261,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 template <int BN>
 static int launch_pair_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
-  static unsigned long long attr_set_mask = 0ull;
+  static std::atomic<unsigned long long> attr_set_mask{0ull};  // engines of several host threads may launch concurrently
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
-  if (!((attr_set_mask >> dev) & 1ull)) {
+  if (!((attr_set_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BN>::DYN_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set_mask |= 1ull << dev;
+    attr_set_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
   const int total_pairs = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN) / 2;
   const int sm_pairs = num_sms / 2;

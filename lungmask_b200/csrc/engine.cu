@@ -171,7 +171,8 @@ struct lm_engine {
   DevBuf<uint8_t> d_lps_out, d_native_l, d_native_r;
   DevBuf<int32_t> d_boxes;
   DevBuf<uint8_t> d_labels, d_post, d_out, d_out2, d_fused, d_mask;
-  DevBuf<float> d_scores;
+  DevBuf<float> d_scores, d_norm;
+  DevBuf<uint8_t> d_fvol;   // float volumes (float32 / float64), raw bytes
   DevBuf<uint32_t> d_scratch;
   PostScratch post;
   cudaEvent_t ev[8] = {};
@@ -231,11 +232,16 @@ int upload(float** dst, const float* src, size_t n, cudaStream_t st) {
   return (int)cudaStreamSynchronize(st);
 }
 
-int forward_batch(lm_engine* e, Slot& s, const int16_t* d_resized, int n, uint8_t* d_labels, float* d_scores,
+// d_in: the resized slices, int16 HU (in_f32 == false) or the normalised fp32 network input of a float volume
+int forward_batch(lm_engine* e, Slot& s, const void* d_in, bool in_f32, int n, uint8_t* d_labels, float* d_scores,
                   bool time_convs) {
   int* const range = e->d_range + (size_t)(&s - e->slots) * RANGE_STRIDE;
-  RC((e->stem_v2 ? launch_stem_v2 : launch_stem)(d_resized, e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
-                                                 range + A0, s.act_scale[A0], e->num_sms, e->st));
+  if (in_f32)
+    RC(launch_stem_f32(static_cast<const float*>(d_in), e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
+                       range + A0, s.act_scale[A0], e->stem_v2, e->num_sms, e->st));
+  else
+    RC((e->stem_v2 ? launch_stem_v2 : launch_stem)(static_cast<const int16_t*>(d_in), e->act[A0], s.stem_w, s.stem_bias, s.stem_scale,
+                                                   s.stem_shift, n, R, R, range + A0, s.act_scale[A0], e->num_sms, e->st));
   e->launches++;
   int up = 0;
   for (int i = 0; i < NUM_LAYERS; ++i) {
@@ -282,8 +288,8 @@ int drain_conv_events(lm_engine* e) {
   return 0;
 }
 
-int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t* d_labels, float* h_scores,
-                float* conv_ms) {
+int forward_all(lm_engine* e, int slot, const void* d_in, int S, uint8_t* d_labels, float* h_scores,
+                float* conv_ms, bool in_f32 = false) {
   if (slot < 0 || slot >= LM_MAX_SLOTS || !e->slots[slot].loaded) return fail(-30, "weight slot %d not loaded", slot);
   Slot& s = e->slots[slot];
   float* d_scores = nullptr;
@@ -293,8 +299,9 @@ int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t
   }
   for (int s0 = 0; s0 < S; s0 += e->B) {
     const int n = S - s0 < e->B ? S - s0 : e->B;
-    RC(forward_batch(e, s, d_resized + (size_t)s0 * R * R, n, d_labels + (size_t)s0 * R * R, d_scores,
-                     conv_ms != nullptr || e->time_convs));
+    const void* in_wave = in_f32 ? static_cast<const void*>(static_cast<const float*>(d_in) + (size_t)s0 * R * R)
+                                 : static_cast<const void*>(static_cast<const int16_t*>(d_in) + (size_t)s0 * R * R);
+    RC(forward_batch(e, s, in_wave, in_f32, n, d_labels + (size_t)s0 * R * R, d_scores, conv_ms != nullptr || e->time_convs));
     if (h_scores) {
       CU(cudaMemcpyAsync(h_scores + (size_t)s0 * s.K * R * R, d_scores, (size_t)n * s.K * R * R * sizeof(float),
                          cudaMemcpyDeviceToHost, e->st));
@@ -312,18 +319,26 @@ int forward_all(lm_engine* e, int slot, const int16_t* d_resized, int S, uint8_t
 }
 
 // preprocess -> forward -> postprocess -> reshape, all device-resident. d_out: (S,H,W) uint8.
-int inference_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int W, int flags, uint8_t* d_out) {
+// vtype: 0 = int16 HU volume, 1 = float32, 2 = float64 (float volumes keep their dtype through the reference's
+// pre-processing and normalisation; preproc.cu resize_kernel)
+int inference_dev(lm_engine* e, int slot, const void* d_vol, int S, int H, int W, int flags, uint8_t* d_out, int vtype = 0) {
   const size_t nr = (size_t)S * R * R;
   RC(e->d_boxes.reserve((size_t)S * 4));
-  RC(e->d_resized.reserve(nr));
+  if (vtype == 0) RC(e->d_resized.reserve(nr)); else RC(e->d_norm.reserve(nr));
   RC(e->d_labels.reserve(nr));
   RC(e->d_post.reserve(nr));
   CU(cudaEventRecord(e->ev[1], e->st));
-  RC(launch_bodymask(d_vol, S, H, W, e->d_boxes.p, nullptr, e->num_sms, e->st));
-  RC(launch_resize(d_vol, S, H, W, e->d_boxes.p, e->d_resized.p, R, R, 1, e->num_sms, e->st));
+  if (vtype == 0) {
+    RC(launch_bodymask(static_cast<const int16_t*>(d_vol), S, H, W, e->d_boxes.p, nullptr, e->num_sms, e->st));
+    RC(launch_resize(static_cast<const int16_t*>(d_vol), S, H, W, e->d_boxes.p, e->d_resized.p, R, R, 1, e->num_sms, e->st));
+  } else {
+    RC(launch_bodymask_float(d_vol, vtype == 2, S, H, W, e->d_boxes.p, nullptr, e->num_sms, e->st));
+    RC(launch_resize_float(d_vol, vtype == 2, S, H, W, e->d_boxes.p, e->d_norm.p, R, R, e->num_sms, e->st));
+  }
   e->launches += 2;
   CU(cudaEventRecord(e->ev[2], e->st));
-  RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, nullptr, nullptr));
+  if (vtype == 0) RC(forward_all(e, slot, e->d_resized.p, S, e->d_labels.p, nullptr, nullptr));
+  else RC(forward_all(e, slot, e->d_norm.p, S, e->d_labels.p, nullptr, nullptr, true));
   CU(cudaEventRecord(e->ev[3], e->st));
   const uint8_t* masks = e->d_labels.p;
   if (!(flags & LM_FLAG_NO_POSTPROCESS)) {
@@ -536,6 +551,7 @@ void lm_destroy(lm_engine* e) {
     cudaFree(s.stem_w); cudaFree(s.stem_bias); cudaFree(s.stem_scale); cudaFree(s.stem_shift); cudaFree(s.head_w); cudaFree(s.head_b);
     for (auto& l : s.lw) { cudaFree(l.w); cudaFree(l.bias); cudaFree(l.scale); cudaFree(l.shift); }
   }
+  e->d_norm.release(); e->d_fvol.release();
   e->d_native.release(); e->d_lps_out.release(); e->d_native_l.release(); e->d_native_r.release();
   e->d_vol.release(); e->d_resized.release(); e->d_boxes.release(); e->d_labels.release(); e->d_post.release();
   e->d_out.release(); e->d_out2.release(); e->d_fused.release(); e->d_mask.release(); e->d_scores.release(); e->d_scratch.release();
@@ -674,13 +690,13 @@ int lm_apply_volume(lm_engine* e, int slot, const int16_t* vol, int S, int H, in
 }
 
 // LMInferer.apply with a fill model on a device-resident volume: res_l / res_r in engine buffers, result to d_final
-static int fused_enqueue(lm_engine* e, int slot_base, int slot_fill, const int16_t* d_vol, int S, int H, int W, int flags,
-                         uint8_t* d_final) {
+static int fused_enqueue(lm_engine* e, int slot_base, int slot_fill, const void* d_vol, int S, int H, int W, int flags,
+                         uint8_t* d_final, int vtype = 0) {
   // both inner inferences honour volume_postprocessing (mask.py:191-194); the fusion post-processing below does not
   const int inner = flags & LM_FLAG_NO_POSTPROCESS;
   const size_t n = (size_t)S * H * W;
-  RC(inference_dev(e, slot_base, d_vol, S, H, W, inner, e->d_out.p));   // res_l (mask.py:225)
-  RC(inference_dev(e, slot_fill, d_vol, S, H, W, inner, e->d_out2.p));  // res_r (mask.py:227)
+  RC(inference_dev(e, slot_base, d_vol, S, H, W, inner, e->d_out.p, vtype));   // res_l (mask.py:225)
+  RC(inference_dev(e, slot_fill, d_vol, S, H, W, inner, e->d_out2.p, vtype));  // res_r (mask.py:227)
   RC(fuse_device(e->d_out.p, e->d_out2.p, n, e->d_scratch.p, e->d_spare, e->num_sms, e->st));  // spare stays on the device
   e->launches += 3;
   // labels after the fusion are <= K_base (the spare value is max + 1 <= K_base): mask.py:232
@@ -730,6 +746,52 @@ int lm_apply_fused_dev(lm_engine* e, int slot_base, int slot_fill, const int16_t
     return 0;
   }));
   collect_timings(e);
+  return 0;
+}
+
+int lm_apply_volume_float(lm_engine* e, int slot, int slot_fill, const void* vol, int is_f64, int S, int H, int W, int flags,
+                          uint8_t* out) {
+  if (!e || !vol || !out) return fail(-1, "lm_apply_volume_float: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_apply_volume_float: empty volume");
+  if (slot < 0 || slot >= LM_MAX_SLOTS || !e->slots[slot].loaded) return fail(-30, "weight slot %d not loaded", slot);
+  const bool fused = slot_fill >= 0;
+  if (fused && (slot_fill >= LM_MAX_SLOTS || !e->slots[slot_fill].loaded)) return fail(-30, "weight slot %d not loaded", slot_fill);
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W, esz = is_f64 ? 8 : 4;
+  RC(e->d_fvol.reserve(n * esz));
+  RC(e->d_out.reserve(n));
+  if (fused) { RC(e->d_out2.reserve(n)); RC(e->d_fused.reserve(n)); }
+  const int vtype = is_f64 ? 2 : 1;
+  RC(run_checked(e, [&]() -> int {
+    e->launches = 0;
+    e->ev_used = 0;
+    CU(cudaEventRecord(e->ev[0], e->st));
+    CU(cudaMemcpyAsync(e->d_fvol.p, vol, n * esz, cudaMemcpyHostToDevice, e->st));
+    const uint8_t* result = e->d_out.p;
+    if (fused) { RC(fused_enqueue(e, slot, slot_fill, e->d_fvol.p, S, H, W, flags, e->d_fused.p, vtype)); result = e->d_fused.p; }
+    else RC(inference_dev(e, slot, e->d_fvol.p, S, H, W, flags, e->d_out.p, vtype));
+    CU(cudaMemcpyAsync(out, result, n, cudaMemcpyDeviceToHost, e->st));
+    CU(cudaEventRecord(e->ev[6], e->st));
+    return 0;
+  }));
+  collect_timings(e);
+  return 0;
+}
+
+int lm_preprocess_float(lm_engine* e, const void* vol, int is_f64, int S, int H, int W, float* normalised, int32_t* boxes) {
+  if (!e || !vol || !normalised || !boxes) return fail(-1, "lm_preprocess_float: NULL argument");
+  if (S < 1 || H < 1 || W < 1) return fail(-1, "lm_preprocess_float: empty volume");
+  CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)S * H * W, esz = is_f64 ? 8 : 4, nr = (size_t)S * R * R;
+  RC(e->d_fvol.reserve(n * esz));
+  RC(e->d_boxes.reserve((size_t)S * 4));
+  RC(e->d_norm.reserve(nr));
+  CU(cudaMemcpyAsync(e->d_fvol.p, vol, n * esz, cudaMemcpyHostToDevice, e->st));
+  RC(launch_bodymask_float(e->d_fvol.p, is_f64, S, H, W, e->d_boxes.p, nullptr, e->num_sms, e->st));
+  RC(launch_resize_float(e->d_fvol.p, is_f64, S, H, W, e->d_boxes.p, e->d_norm.p, R, R, e->num_sms, e->st));
+  CU(cudaMemcpyAsync(normalised, e->d_norm.p, nr * sizeof(float), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaMemcpyAsync(boxes, e->d_boxes.p, (size_t)S * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, e->st));
+  CU(cudaStreamSynchronize(e->st));
   return 0;
 }
 

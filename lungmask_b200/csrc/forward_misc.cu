@@ -40,7 +40,18 @@ __device__ __forceinline__ void split_store(const float* v, op_t* hi_dst, op_t* 
   *reinterpret_cast<uint4*>(lo_dst) = l;
 }
 
-__global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ in, op_t* __restrict__ out,
+// network input of one sample: int16 HU -> (hu + 1024) / 1624 through the table (mask.py:167-168: float64 division, then
+// the cast to fp32); float volumes arrive already normalised (preproc.cu resize_kernel<float / double>)
+__device__ __forceinline__ float stem_input(const int16_t* img, size_t idx, const float* lut) {
+  int hu = img[idx];
+  hu = hu > 600 ? 600 : hu;  // mask.py:167 (no-op after the clip in utils.py:45)
+  const int i = hu + 1024;
+  return i >= 0 ? lut[i] : (float)((double)i / 1624.0);  // mask.py:168 (values below -1024 never come out of preprocess)
+}
+__device__ __forceinline__ float stem_input(const float* img, size_t idx, const float*) { return img[idx]; }
+
+template <typename IT>
+__global__ void __launch_bounds__(256) stem_kernel(const IT* __restrict__ in, op_t* __restrict__ out,
                                                    const float* __restrict__ w,      // [64][9]
                                                    const float* __restrict__ bias,   // [64]
                                                    const float* __restrict__ scale,  // [64]
@@ -69,12 +80,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
     for (int tap = 0; tap < 9; ++tap) {
       const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
       float val = 0.f;
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        int hu = in[(size_t)n * plane + (size_t)yy * W + xx];
-        hu = hu > 600 ? 600 : hu;  // mask.py:167 (no-op after the clip in utils.py:45)
-        const int idx = hu + 1024;
-        val = idx >= 0 ? lut[idx] : (float)((double)idx / 1624.0);  // mask.py:168 (values below -1024 never come out of preprocess)
-      }
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = stem_input(in, (size_t)n * plane + (size_t)yy * W + xx, lut);
       v[tap] = val;
     }
     float yv[CPT];
@@ -98,8 +104,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const int16_t* __restrict__ i
 // pixel, 15 % of the HBM write rate).  Here a thread owns ONE group of CPT output channels for the whole kernel, keeps
 // that group's 9 x CPT weights and 3 x CPT epilogue constants in registers, and walks quads of 4 x-adjacent pixels with
 // an 18-sample (3 x 6) input window: 4.5 LUT loads per pixel and no weight loads.
-template <int QW>
-__global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict__ in, op_t* __restrict__ out,
+template <int QW, typename IT>
+__global__ void __launch_bounds__(128) stem_kernel_v2(const IT* __restrict__ in, op_t* __restrict__ out,
                                                       const float* __restrict__ w,      // [64][9]
                                                       const float* __restrict__ bias,   // [64]
                                                       const float* __restrict__ scale,  // [64]
@@ -130,7 +136,7 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict_
     const int y = (int)(rowid % H);
     const int n = (int)(rowid / H);
     const int x0 = qx * QW;
-    const int16_t* img = in + (size_t)n * plane;
+    const IT* img = in + (size_t)n * plane;
     float win[3][QW + 2];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
@@ -139,12 +145,7 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const int16_t* __restrict_
       for (int dx = 0; dx < QW + 2; ++dx) {
         const int xx = x0 + dx - 1;
         float val = 0.f;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          int hu = img[(size_t)yy * W + xx];
-          hu = hu > 600 ? 600 : hu;  // mask.py:167
-          const int idx = hu + 1024;
-          val = idx >= 0 ? lut[idx] : (float)((double)idx / 1624.0);  // mask.py:168
-        }
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = stem_input(img, (size_t)yy * W + xx, lut);
         win[dy][dx] = val;
       }
     }
@@ -308,24 +309,35 @@ inline int grid_for(size_t total, int block, int num_sms) {
 
 }  // namespace
 
-int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
-                const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream) {
-  const size_t total = (size_t)N * H * W * (64 / CPT);
-  stem_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag, out_scale);
+template <typename IT>
+static int launch_stem_t(const IT* in, void* out, const float* w, const float* bias, const float* scale, const float* shift, int N,
+                         int H, int W, int* range_flag, float out_scale, int v2, int num_sms, cudaStream_t stream) {
+  constexpr int QW = 4;
+  if (v2 && W % QW == 0) {
+    const size_t threads = (size_t)N * H * (W / QW) * (64 / CPT);
+    size_t blocks = (threads + 127) / 128;
+    const size_t cap = (size_t)num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    stem_kernel_v2<QW, IT><<<(int)blocks, 128, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag, out_scale);
+  } else {
+    const size_t total = (size_t)N * H * W * (64 / CPT);
+    stem_kernel<IT><<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag, out_scale);
+  }
   return (int)cudaGetLastError();
 }
 
+int launch_stem(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
+                const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream) {
+  return launch_stem_t<int16_t>(in, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, 0, num_sms, stream);
+}
 int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
                    const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream) {
-  constexpr int QW = 4;
-  if (W % QW) return launch_stem(in, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, num_sms, stream);
-  const size_t threads = (size_t)N * H * (W / QW) * (64 / CPT);
-  size_t blocks = (threads + 127) / 128;
-  const size_t cap = (size_t)num_sms * 8;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  stem_kernel_v2<QW><<<(int)blocks, 128, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag, out_scale);
-  return (int)cudaGetLastError();
+  return launch_stem_t<int16_t>(in, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, 1, num_sms, stream);
+}
+int launch_stem_f32(const float* in_norm, void* out, const float* w, const float* bias, const float* scale, const float* shift, int N,
+                    int H, int W, int* range_flag, float out_scale, int v2, int num_sms, cudaStream_t stream) {
+  return launch_stem_t<float>(in_norm, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, v2, num_sms, stream);
 }
 
 int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,

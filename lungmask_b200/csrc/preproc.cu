@@ -10,6 +10,7 @@
 // the nearest-neighbour up-scaled mask - computed on the thumbnail through the monotone index maps, so the
 // full-resolution mask is never materialised (it is written only when a caller asks for it).
 // resize_kernel: one thread per output pixel, float64 coordinates and accumulation order as scipy's zoom.
+#include <atomic>
 #include "preproc.cuh"
 
 namespace lm {
@@ -91,8 +92,9 @@ __device__ __forceinline__ bool bit_at(const uint32_t (*b)[WORDS], int r, int c)
   return (b[r][c >> 5] >> (c & 31)) & 1u;
 }
 
+template <typename VT>
 __global__ void __launch_bounds__(NTHREADS, 1)
-bodymask_kernel(const int16_t* __restrict__ vol, int S, int H, int W, int32_t* __restrict__ boxes,
+bodymask_kernel(const VT* __restrict__ vol, int S, int H, int W, int32_t* __restrict__ boxes,
                 uint8_t* __restrict__ mask_out) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -100,7 +102,7 @@ bodymask_kernel(const int16_t* __restrict__ vol, int S, int H, int W, int32_t* _
   const int wr = tid / WORDS, wk = tid % WORDS;  // this thread's mask word: row wr, word wk
 
   for (int s = blockIdx.x; s < S; s += gridDim.x) {
-    const int16_t* img = vol + (size_t)s * H * W;
+    const VT* img = vol + (size_t)s * H * W;
     const AxisMap dn_y = make_axis(H, T), dn_x = make_axis(W, T);  // zoom(img, 128/shape, order=0), utils.py:68
     const AxisMap up_y = make_axis(T, H), up_x = make_axis(T, W);  // zoom(mask, shape/128, order=0), utils.py:81-82
 
@@ -108,8 +110,9 @@ bodymask_kernel(const int16_t* __restrict__ vol, int S, int H, int W, int32_t* _
     for (int w = warp; w < T * WORDS; w += NTHREADS / 32) {
       const int r = w / WORDS, k = w % WORDS, c = k * 32 + lane;
       const int iy = nn_index(dn_y, r), ix = nn_index(dn_x, c);
-      const int v = (iy >= 0 && ix >= 0) ? (int)img[(size_t)iy * W + ix] : 0;
-      const uint32_t word = __ballot_sync(0xffffffffu, v > -500);
+      // (int16 HU, or float HU for float volumes - the reference thresholds whatever dtype it is given)
+      const double v = (iy >= 0 && ix >= 0) ? (double)img[(size_t)iy * W + ix] : 0.0;
+      const uint32_t word = __ballot_sync(0xffffffffu, v > -500.0);
       if (lane == 0) sm.bits[0][r][k] = word;
     }
     __syncthreads();
@@ -265,9 +268,17 @@ bodymask_kernel(const int16_t* __restrict__ vol, int S, int H, int W, int32_t* _
 }
 
 // zoom(crop, 256/crop.shape, order=1) on the clipped HU values, dtype preserved (utils.py:45,107-110).
+// VT = int16: the result is rounded half away from zero to int16 (scipy's cast of an integer output array).
+// VT = float / double (float volumes keep their dtype through the reference's pre-processing, utils.py:44-45,108-110):
+// the interpolated value is cast to VT without rounding to an integer and then normalised as mask.py:167-168 does in
+// that dtype - (x + 1024) / 1624 in float32 arithmetic for float32 volumes, in float64 for float64 - and stored as the
+// fp32 the network receives (mask.py:178-182).
+template <typename VT> struct ResizeOut { using type = float; };
+template <> struct ResizeOut<int16_t> { using type = int16_t; };
+template <typename VT>
 __global__ void __launch_bounds__(256)
-resize_kernel(const int16_t* __restrict__ vol, int S, int H, int W, const int32_t* __restrict__ boxes,
-              int16_t* __restrict__ out, int OH, int OW, int clip) {
+resize_kernel(const VT* __restrict__ vol, int S, int H, int W, const int32_t* __restrict__ boxes,
+              typename ResizeOut<VT>::type* __restrict__ out, int OH, int OW, int clip) {
   const size_t total = (size_t)S * OH * OW;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int s = (int)(t / ((size_t)OH * OW));
@@ -275,17 +286,17 @@ resize_kernel(const int16_t* __restrict__ vol, int S, int H, int W, const int32_
     const int oy = rem / OW, ox = rem - oy * OW;
     const int32_t* b = boxes + 4 * s;
     const int r0 = b[0], c0 = b[1], h = b[2] - b[0], w = b[3] - b[1];
-    const int16_t* img = vol + (size_t)s * H * W;
+    const VT* img = vol + (size_t)s * H * W;
     const double sy = OH > 1 ? __ddiv_rn((double)(h - 1), (double)(OH - 1)) : 0.0;
     const double sx = OW > 1 ? __ddiv_rn((double)(w - 1), (double)(OW - 1)) : 0.0;
     const double ys = __dmul_rn((double)oy, sy), xs = __dmul_rn((double)ox, sx);
-    int16_t res = 0;
-    if (ys <= (double)(h - 1) && xs <= (double)(w - 1)) {
+    double acc = 0.0;
+    const bool inside = ys <= (double)(h - 1) && xs <= (double)(w - 1);
+    if (inside) {
       const double fy0 = floor(ys), fx0 = floor(xs);
       const int y0 = (int)fy0, x0 = (int)fx0;
       const double fy = __dsub_rn(ys, fy0), fx = __dsub_rn(xs, fx0);
       const double wy[2] = {__dsub_rn(1.0, fy), fy}, wx[2] = {__dsub_rn(1.0, fx), fx};
-      double acc = 0.0;
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
@@ -293,19 +304,31 @@ resize_kernel(const int16_t* __restrict__ vol, int S, int H, int W, const int32_
           const int yy = y0 + dy, xx = x0 + dx;
           double v = 0.0;
           if (yy < h && xx < w) {
-            int hu = img[(size_t)(r0 + yy) * W + (c0 + xx)];
-            if (clip) hu = hu < -1024 ? -1024 : (hu > 600 ? 600 : hu);  // np.clip(-1024, 600), utils.py:45
-            v = (double)hu;
+            v = (double)img[(size_t)(r0 + yy) * W + (c0 + xx)];
+            if (clip) v = v < -1024.0 ? -1024.0 : (v > 600.0 ? 600.0 : v);  // np.clip(-1024, 600), utils.py:45 (exact in every dtype)
           }
           acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(v, wy[dy]), wx[dx]));
         }
       }
-      acc = acc > 0.0 ? __dadd_rn(acc, 0.5) : __dsub_rn(acc, 0.5);  // scipy: round half away from zero
-      double tr = trunc(acc);
-      tr = tr < -32768.0 ? -32768.0 : (tr > 32767.0 ? 32767.0 : tr);
-      res = (int16_t)tr;
     }
-    out[t] = res;
+    if constexpr (sizeof(VT) == 2) {
+      int16_t res = 0;
+      if (inside) {
+        acc = acc > 0.0 ? __dadd_rn(acc, 0.5) : __dsub_rn(acc, 0.5);  // scipy: round half away from zero
+        double tr = trunc(acc);
+        tr = tr < -32768.0 ? -32768.0 : (tr > 32767.0 ? 32767.0 : tr);
+        res = (int16_t)tr;
+      }
+      out[t] = res;
+    } else if constexpr (sizeof(VT) == 4) {
+      float x = inside ? (float)acc : 0.f;                    // scipy casts the float64 sum to the float32 output array
+      x = x > 600.f ? 600.f : x;                              // mask.py:167
+      out[t] = __fdiv_rn(__fadd_rn(x, 1024.f), 1624.f);       // mask.py:168 in float32 (numpy keeps the array's dtype)
+    } else {
+      double x = inside ? acc : 0.0;
+      x = x > 600.0 ? 600.0 : x;
+      out[t] = (float)__ddiv_rn(__dadd_rn(x, 1024.0), 1624.0);  // float64 arithmetic, then the cast of mask.py:178-182
+    }
   }
 }
 
@@ -366,29 +389,47 @@ int launch_orient_u8(const uint8_t* src, uint8_t* dst, const int dims_lps[3], co
 
 int preproc_smem_bytes() { return (int)sizeof(Smem); }
 
-int launch_bodymask(const int16_t* vol, int S, int H, int W, int32_t* boxes, uint8_t* mask_out, int num_sms,
-                    cudaStream_t stream) {
+template <typename VT>
+static int launch_bodymask_t(const VT* vol, int S, int H, int W, int32_t* boxes, uint8_t* mask_out, int num_sms, cudaStream_t stream) {
   if (H < 1 || W < 1 || H > 16384 || W > 16384) return -10;
-  static unsigned long long attr_set_mask = 0ull;  // the dynamic shared-memory opt-in is a per-device function attribute
+  static std::atomic<unsigned long long> attr_set_mask{0ull};  // engines of several host threads may launch concurrently  // the dynamic shared-memory opt-in is a per-device function attribute
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
-  if (!((attr_set_mask >> dev) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(bodymask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (!((attr_set_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(bodymask_kernel<VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
-    attr_set_mask |= 1ull << dev;
+    attr_set_mask.fetch_or(1ull << dev, std::memory_order_release);   // (benign race: setting the attribute twice is harmless)
   }
   const int grid = S < num_sms ? S : num_sms;
-  bodymask_kernel<<<grid, NTHREADS, sizeof(Smem), stream>>>(vol, S, H, W, boxes, mask_out);
+  bodymask_kernel<VT><<<grid, NTHREADS, sizeof(Smem), stream>>>(vol, S, H, W, boxes, mask_out);
   return (int)cudaGetLastError();
 }
+int launch_bodymask(const int16_t* vol, int S, int H, int W, int32_t* boxes, uint8_t* mask_out, int num_sms, cudaStream_t stream) {
+  return launch_bodymask_t<int16_t>(vol, S, H, W, boxes, mask_out, num_sms, stream);
+}
+int launch_bodymask_float(const void* vol, int is_f64, int S, int H, int W, int32_t* boxes, uint8_t* mask_out, int num_sms,
+                          cudaStream_t stream) {
+  return is_f64 ? launch_bodymask_t<double>(static_cast<const double*>(vol), S, H, W, boxes, mask_out, num_sms, stream)
+                : launch_bodymask_t<float>(static_cast<const float*>(vol), S, H, W, boxes, mask_out, num_sms, stream);
+}
 
-int launch_resize(const int16_t* vol, int S, int H, int W, const int32_t* boxes, int16_t* out, int OH, int OW, int clip,
-                  int num_sms, cudaStream_t stream) {
+template <typename VT>
+static int launch_resize_t(const VT* vol, int S, int H, int W, const int32_t* boxes, typename ResizeOut<VT>::type* out, int OH, int OW,
+                           int clip, int num_sms, cudaStream_t stream) {
   const size_t total = (size_t)S * OH * OW;
   size_t g = (total + 255) / 256;
   if (g > (size_t)num_sms * 32) g = (size_t)num_sms * 32;
-  resize_kernel<<<(int)g, 256, 0, stream>>>(vol, S, H, W, boxes, out, OH, OW, clip);
+  resize_kernel<VT><<<(int)g, 256, 0, stream>>>(vol, S, H, W, boxes, out, OH, OW, clip);
   return (int)cudaGetLastError();
+}
+int launch_resize(const int16_t* vol, int S, int H, int W, const int32_t* boxes, int16_t* out, int OH, int OW, int clip,
+                  int num_sms, cudaStream_t stream) {
+  return launch_resize_t<int16_t>(vol, S, H, W, boxes, out, OH, OW, clip, num_sms, stream);
+}
+int launch_resize_float(const void* vol, int is_f64, int S, int H, int W, const int32_t* boxes, float* out_norm, int OH, int OW,
+                        int num_sms, cudaStream_t stream) {
+  return is_f64 ? launch_resize_t<double>(static_cast<const double*>(vol), S, H, W, boxes, out_norm, OH, OW, 1, num_sms, stream)
+                : launch_resize_t<float>(static_cast<const float*>(vol), S, H, W, boxes, out_norm, OH, OW, 1, num_sms, stream);
 }
 
 }  // namespace lm

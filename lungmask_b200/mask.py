@@ -89,17 +89,30 @@ def get_model(modelname: str, modelpath: Optional[str] = None) -> NativeModel:
 
 
 def _to_int16_volume(image: np.ndarray) -> np.ndarray:
-    """The engine computes on int16 HU.  Integer inputs of any width give the same result as the
-    reference because it clips to [-1024, 600] before resampling (utils.py:45) and thresholds at
-    -500 HU; floating-point volumes would be resampled without rounding by the reference
-    (utils.py:108-110 keeps the dtype) and are not supported."""
+    """Integer volumes.  Integers of any width give the same result as the reference because it clips to [-1024, 600]
+    before resampling (utils.py:45) and thresholds at -500 HU, so they are clipped into int16 here."""
     if image.ndim != 3:
         raise ValueError("expected a (slices, H, W) volume, got shape %s" % (image.shape,))
     if image.dtype == np.int16:
         return np.ascontiguousarray(image)
-    if np.issubdtype(image.dtype, np.integer):
+    if np.issubdtype(image.dtype, np.integer) or image.dtype == bool:
         return np.clip(image, -1024, 600).astype(np.int16)
-    raise TypeError("lungmask_b200 needs an integer HU volume (got %s); cast/round it first" % image.dtype)
+    raise TypeError("not an integer volume: %s" % image.dtype)
+
+
+def _to_engine_volume(image: np.ndarray) -> np.ndarray:
+    """The array the engine receives: int16 for integer volumes; float32 / float64 volumes keep their dtype, as they do
+    in the reference (utils.preprocess clips and resamples in the input dtype and mask.py:167-168 normalises in it; the
+    engine has a float path for exactly that).  Other float widths are widened to float32 (the reference would compute
+    in float16 / longdouble there: documented deviation)."""
+    if image.ndim != 3:
+        raise ValueError("expected a (slices, H, W) volume, got shape %s" % (image.shape,))
+    if image.dtype in (np.float32, np.float64):
+        return np.ascontiguousarray(image)
+    if np.issubdtype(image.dtype, np.floating):
+        logger.warning("volume dtype %s is computed as float32", image.dtype)
+        return np.ascontiguousarray(image, dtype=np.float32)
+    return _to_int16_volume(image)
 
 
 class LMInferer:
@@ -164,12 +177,20 @@ class LMInferer:
             return None
 
     def _run(self, volume: np.ndarray, code: str = "LPS") -> np.ndarray:
-        vol = _to_int16_volume(volume)
+        vol = _to_engine_volume(volume)
         fused = self.fillmodel is not None
         if fused:
             logger.info(f"Apply: {self.modelname}")
             logger.info(f"Apply: {self.fillmodel}")
             logger.info("Fusing results... this may take up to several minutes!")
+        if vol.dtype != np.int16:   # float volume
+            if code != "LPS":       # re-orient on the host (rare: float + non-LPS); the integer path does it on the device
+                res = self.engine.apply_volume_float(0, orient.to_lps(vol, code), slot_fill=-1 if not fused else 1,
+                                                     postprocess=self.volume_postprocessing)
+                if not fused:
+                    return orient.from_lps(res, code)
+                raise NotImplementedError("fusion of a float volume in a non-LPS orientation: re-orient the image first")
+            return self.engine.apply_volume_float(0, vol, slot_fill=1 if fused else -1, postprocess=self.volume_postprocessing)
         if code == "LPS":
             if not fused:
                 return self.engine.apply_volume(0, vol, postprocess=self.volume_postprocessing)

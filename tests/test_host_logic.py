@@ -51,14 +51,18 @@ def test_no_silent_cpu_fallback():
             _native.Engine(0, 2)
 
 
-def test_int16_conversion_rules():
-    from lungmask_b200.mask import _to_int16_volume
+def test_volume_dtype_rules():
+    from lungmask_b200.mask import _to_engine_volume, _to_int16_volume
     v = np.array([[[-3000, 0, 70000]]], dtype=np.int32)
     assert _to_int16_volume(v).tolist() == [[[-1024, 0, 600]]]
+    assert _to_engine_volume(v).dtype == np.int16
+    for dt in (np.float32, np.float64):          # float volumes keep their dtype (the reference computes in it)
+        assert _to_engine_volume(v.astype(dt)).dtype == dt
+    assert _to_engine_volume(v.astype(np.float16)).dtype == np.float32
     with pytest.raises(TypeError):
         _to_int16_volume(v.astype(np.float64))
     with pytest.raises(ValueError):
-        _to_int16_volume(np.zeros((4, 4), np.int16))
+        _to_engine_volume(np.zeros((4, 4), np.int16))
 
 
 def test_native_binding_refuses_lossy_conversions():
