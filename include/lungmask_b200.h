@@ -169,6 +169,9 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * layers, 2 for the wide ones), "dual_issue" (0/1: a second MMA-issuing thread per CTA on alternate chunks;
  * default 0), "cta_pairs" (0/1: the experimental cta_group::2 convolution kernel; default 0),
  * "stem_v2" (0/1: the experimental register-resident stem kernel; default 0),
+ * "graphs" (1, default: a volume's forward - every wave's ~26 launches - is captured once as a CUDA graph and replayed;
+ * 0: every kernel is launched individually; per-launch convolution timing and score taps always launch individually),
+ * "upsample_v2" (0/1: cell-centred bilinear upsample kernel),
  * "ccl_rule" (1 = pruned neighbour rule of the 26-connected labelling, the default; 0 = probe all 13 backward
  * neighbours), "post_region_capacity" (test hook: size of the post-processing's region tables),
  * "post_debug_stage" (parity taps of the post-processing). */

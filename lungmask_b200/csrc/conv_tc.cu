@@ -123,6 +123,9 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
   mbar_wait(g.afull0, 0);
   if (is_mine(0)) mbar_wait(g.tempty0, 1);
   mbar_wait(g.full0, 0);
+#ifdef LM_CONV_PROFILE
+  const long long prof_issue_t0 = clock64();
+#endif
 
   for (int tile = g.first_tile; tile < g.total_tiles; tile += g.tile_step) {
     const bool last_tile = tile + g.tile_step >= g.total_tiles;
@@ -169,9 +172,9 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
             has_next = !last_tile;
             kb_left = num_kb; cit = 0; ++tseq;   // (kc is 0 here: a tile's last k-block closes its chunk)
           }
-          if (has_next) mbar_wait(g.afull0 + 8 * ab, aph);
+          if (has_next) { LM_PROF_T0(); mbar_wait(g.afull0 + 8 * ab, aph); LM_PROF_ADD(3); }
         }
-        if (has_next) mbar_wait(g.full0 + 8 * s, ph);
+        if (has_next) { LM_PROF_T0(); mbar_wait(g.full0 + 8 * s, ph); LM_PROF_ADD(4); }
         // ---- rest of the burst, then the releases
         if (mine) {
 #pragma unroll
@@ -187,10 +190,13 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
         // the accumulator slot of the next chunk is awaited LAST: with a two-slot ring it is the one hand-shake that
         // regularly blocks (the epilogue drains chunk i-1 while chunk i executes), and blocking in the middle of the
         // burst would leave the tensor pipe with half a k-block queued (measured: 8 % slower on the BN = 128 layers)
-        if (has_next && kc == 0 && is_mine(gc)) mbar_wait(g.tempty0 + 8 * (gc % NBUF), (((gc / NBUF) & 1u) ^ 1u));
+        if (has_next && kc == 0 && is_mine(gc)) { LM_PROF_T0(); mbar_wait(g.tempty0 + 8 * (gc % NBUF), (((gc / NBUF) & 1u) ^ 1u)); LM_PROF_ADD(2); }
       }
     }
   }
+#ifdef LM_CONV_PROFILE
+  atomicAdd(&g_conv_prof[5], (unsigned long long)(clock64() - prof_issue_t0));   // the issuer's whole loop (waits included)
+#endif
 }
 
 template <int BN>
@@ -445,6 +451,14 @@ static int launch_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, c
 void conv_prof_reset() { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z)); }
 void conv_prof_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_conv_prof, 16 * sizeof(unsigned long long)); }
 #endif
+
+// Sets the kernels' > 48 KB dynamic shared-memory opt-in on the current device (lm_create calls it, so that no launch -
+// in particular none inside a CUDA-graph capture - has to).
+int conv_tc_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::DYN_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::DYN_SMEM);
+  return (int)e;
+}
 
 int launch_conv_tc(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   if (p.mode == kModeHead && (p.Cout != 64 || p.K > MAX_CLASSES)) return -4;

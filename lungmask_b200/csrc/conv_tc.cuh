@@ -92,6 +92,10 @@ int launch_conv_tc(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaS
 // CTA-pair variant (conv_tc_pair.cu, tcgen05 cta_group::2; experimental, see the file header). Same contract.
 int launch_conv_tc_pair(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream);
 
+// Per-device preparation (dynamic shared-memory opt-in of every kernel variant); returns a cudaError_t value.
+int conv_tc_prepare();
+int conv_tc_pair_prepare();
+
 // BN (output-channel tile) chosen for a given Cout.
 inline int conv_tile_n(int cout) { return cout >= 128 ? 128 : 64; }
 

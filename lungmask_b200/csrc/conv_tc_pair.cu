@@ -33,8 +33,19 @@
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
 
+namespace lm {
+#ifdef LM_CONV_PROFILE
+// role-level stall accounting for tools/conv_probe (this translation unit's own counters: no relocatable device code)
+__device__ unsigned long long g_conv_prof[16];
+#endif
+}  // namespace lm
+#ifdef LM_CONV_PROFILE
+#define LM_PROF_T0() const long long prof_t0_ = clock64()
+#define LM_PROF_ADD(slot) atomicAdd(&g_conv_prof[slot], (unsigned long long)(clock64() - prof_t0_))
+#else
 #define LM_PROF_T0()
 #define LM_PROF_ADD(slot)
+#endif
 #undef LM_EXP
 #define LM_EXP 0
 #include "conv_tc_common.cuh"
@@ -77,6 +88,9 @@ __device__ __forceinline__ void mma_issue_loop_pair(const IssueArgs& g) {
   mbar_wait(g.afull0, 0);
   mbar_wait(g.tempty0, 1);
   mbar_wait(g.full0, 0);
+#ifdef LM_CONV_PROFILE
+  const long long prof_issue_t0 = clock64();
+#endif
 
   for (int pt = g.first_pair; pt < g.total_pairs; pt += g.pair_step) {
     const bool last_tile = pt + g.pair_step >= g.total_pairs;
@@ -117,9 +131,9 @@ __device__ __forceinline__ void mma_issue_loop_pair(const IssueArgs& g) {
             has_next = !last_tile;
             kb_left = num_kb; cit = 0; ++tseq;
           }
-          if (has_next) mbar_wait(g.afull0 + 8 * ab, aph);
+          if (has_next) { LM_PROF_T0(); mbar_wait(g.afull0 + 8 * ab, aph); LM_PROF_ADD(3); }
         }
-        if (has_next) mbar_wait(g.full0 + 8 * s, ph);
+        if (has_next) { LM_PROF_T0(); mbar_wait(g.full0 + 8 * s, ph); LM_PROF_ADD(4); }
         // ---- rest of the burst, then the releases (to both CTAs)
 #pragma unroll
         for (int k = 2; k < ROW_BYTES / 32; ++k) {
@@ -130,10 +144,13 @@ __device__ __forceinline__ void mma_issue_loop_pair(const IssueArgs& g) {
         umma_commit_pair(g.empty0 + 8 * s_cur, BOTH);
         if (chunk_end) umma_commit_pair(tfull_cur, BOTH);
         if (tap == TAPS - 1) umma_commit_pair(g.aempty0 + 8 * ab_cur, BOTH);
-        if (has_next && kc == 0) mbar_wait(g.tempty0 + 8 * (gc % NBUF), (((gc / NBUF) & 1u) ^ 1u));
+        if (has_next && kc == 0) { LM_PROF_T0(); mbar_wait(g.tempty0 + 8 * (gc % NBUF), (((gc / NBUF) & 1u) ^ 1u)); LM_PROF_ADD(2); }
       }
     }
   }
+#ifdef LM_CONV_PROFILE
+  atomicAdd(&g_conv_prof[5], (unsigned long long)(clock64() - prof_issue_t0));   // the issuer's whole loop (waits included)
+#endif
 }
 
 template <int BN>
@@ -197,6 +214,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   cluster_sync_all();  // the peer's barriers are initialised before any remote arrive / multicast commit / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+#ifdef LM_CONV_PROFILE
+  const long long prof_kernel_t0 = clock64();
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -206,7 +226,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const TileCoord t = decode_tile(my_tile(pq), n_tiles, tiles_x, tiles_img, BN);
       int c = 0;
       for (int cb = 0; cb < num_cb; ++cb, c += BK) {
-        mbar_wait(aempty0 + 8 * ab, aph ^ 1);  // this CTA's buffer is free (multicast commit of the pair's MMAs)
+        { LM_PROF_T0(); mbar_wait(aempty0 + 8 * ab, aph ^ 1); if (lane == 0 && rank == 0) LM_PROF_ADD(0); }  // this CTA's buffer is free (multicast commit of the pair's MMAs)
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx_leader(afull0 + 8 * ab, 2u * a_tx);  // both CTAs' patches
           else           mbar_arrive_leader(afull0 + 8 * ab);
@@ -217,7 +237,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         __syncwarp();
         if (++ab == NUM_A_BUFS) { ab = 0; aph ^= 1; }
         for (int tap = 0; tap < taps; ++tap) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          { LM_PROF_T0(); mbar_wait(empty0 + 8 * s, ph ^ 1); if (lane == 0 && rank == 0) LM_PROF_ADD(1); }
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx_leader(full0 + 8 * s, 2u * (uint32_t)C::STAGE_BYTES);
             else           mbar_arrive_leader(full0 + 8 * s);
@@ -249,6 +269,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+#ifdef LM_CONV_PROFILE
+  if (threadIdx.x == 0 && rank == 0) atomicAdd(&g_conv_prof[9], (unsigned long long)(clock64() - prof_kernel_t0));
+#endif
   cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the other may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
@@ -286,6 +309,17 @@ static int launch_pair_impl(const ConvMaps& maps, const ConvParams& p, int num_s
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<BN>, maps.a0, maps.a1, maps.bx, maps.byw, maps.out, maps.pool, p);
   return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
+
+int conv_tc_pair_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::DYN_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_pair_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::DYN_SMEM);
+  return (int)e;
+}
+
+#ifdef LM_CONV_PROFILE
+void conv_prof_reset_pair() { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z)); }
+void conv_prof_read_pair(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_conv_prof, 16 * sizeof(unsigned long long)); }
+#endif
 
 // Same contract as launch_conv_tc (conv_tc.cuh); `maps` must come from make_conv_maps (which also encodes the pair's
 // weight boxes bx / byw).  Requires an even number of pixel tiles (always true: every level has >= 2 tiles per image).

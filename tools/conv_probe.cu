@@ -13,7 +13,7 @@
 
 using namespace lm;
 #ifdef LM_CONV_PROFILE
-namespace lm { void conv_prof_reset(); void conv_prof_read(unsigned long long*); }
+namespace lm { void conv_prof_reset(); void conv_prof_read(unsigned long long*); void conv_prof_reset_pair(); void conv_prof_read_pair(unsigned long long*); }
 #endif
 
 #define CK(x)                                                                         \
@@ -156,7 +156,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   CK(cudaDeviceSynchronize());
   float ms = 0;
 #ifdef LM_CONV_PROFILE
-  conv_prof_reset();
+  if (g_pair) conv_prof_reset_pair(); else conv_prof_reset();
 #endif
   if (reps > 0) {
     CK(cudaEventRecord(e0));
@@ -256,7 +256,12 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
   }
 #ifdef LM_CONV_PROFILE
   if (reps > 0) {
-    unsigned long long pr[16]; conv_prof_read(pr);
+    unsigned long long pr[16];
+    if (g_pair) {   // counters of the pair's LEADER CTA per k-block of ONE tile pair; epilogue counters come from both CTAs
+      conv_prof_read_pair(pr);
+      for (int i = 0; i < 6; ++i) pr[i] *= 2;
+      pr[9] *= 2;
+    } else conv_prof_read(pr);
     const int BNt = conv_tile_n(L.Cout);
     const double tiles = (double)N * (L.H / 16) * (L.W / 8) * (L.Cout / BNt) * reps;
     const double kbs = tiles * (Cin / kBK) * L.taps;
@@ -281,6 +286,7 @@ int main(int argc, char** argv) {
   const int timing_only = argc > 3 ? atoi(argv[3]) : 0;
   g_dual = argc > 4 ? atoi(argv[4]) : 0;
   g_pair = argc > 5 ? atoi(argv[5]) : 0;
+  const int reps = argc > 6 ? atoi(argv[6]) : 3;   // timed repetitions per network layer (0: one untimed launch per layer, for ncu)
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
   printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d cta_pairs %d\n", prop.name, sms, batch, chunk, g_dual, g_pair);
@@ -329,7 +335,7 @@ int main(int argc, char** argv) {
       {"up3.block3+head", 256, 256, 64, 0, 64, 9, kModeHead, 3},
   };
   double total_ms = 0;
-  for (const Layer& L : net) total_ms += run_layer(L, batch, chunk, sms, false, false, 3);
+  for (const Layer& L : net) total_ms += run_layer(L, batch, chunk, sms, false, false, reps);
   printf("TOTAL tensor-core layers: %.3f ms for %d slices -> %.1f slices/s (conv layers only)\n", total_ms, batch,
          batch / total_ms * 1e3);
   printf("conv_probe done\n");
