@@ -172,6 +172,8 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * "graphs" (1, default: a volume's forward - every wave's ~26 launches - is captured once as a CUDA graph and replayed;
  * 0: every kernel is launched individually; per-launch convolution timing and score taps always launch individually),
  * "upsample_v2" (0/1: cell-centred bilinear upsample kernel),
+ * "merge_ctas" (0, default: the region merge loop of utils.py:310-339 runs on one CTA per SM in batches of independent
+ * candidates; 1: the single-CTA sequential loop; n: that many CTAs),
  * "ccl_rule" (1 = pruned neighbour rule of the 26-connected labelling, the default; 0 = probe all 13 backward
  * neighbours), "post_region_capacity" (test hook: size of the post-processing's region tables),
  * "post_debug_stage" (parity taps of the post-processing). */

@@ -591,6 +591,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_UPSAMPLE_V2")) e->upsample_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
+  if (const char* c = getenv("LM_MERGE_CTAS")) e->post.merge_ctas = atoi(c) > 0 ? atoi(c) : 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
   RC(conv_tc_prepare());
   RC(conv_tc_pair_prepare());
@@ -1194,6 +1195,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
   if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value != 0; return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
+  if (!strcmp(key, "merge_ctas")) { if (value < 0) return fail(-1, "merge_ctas must be >= 0"); e->post.merge_ctas = value; return 0; }
   if (!strcmp(key, "post_region_capacity")) {  // test hook: shrink / grow the region tables (exercises the overflow re-run)
     if (value < 1) return fail(-1, "post_region_capacity must be >= 1");
     CU(cudaSetDevice(e->device));

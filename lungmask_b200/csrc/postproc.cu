@@ -22,9 +22,13 @@
 // host synchronisation (one when the bound is unknown); the region tables have a capacity and the device raises a
 // flag when R exceeds it (postprocess_finish -> the caller grows the tables and runs again).
 #include <algorithm>
+#include <atomic>
 #include <vector>
 #include <string.h>
+#include <cooperative_groups.h>
 #include "postproc.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lm {
 namespace {
@@ -458,7 +462,10 @@ struct MergeArgs {
   Dim d;
 };
 
-__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
+// The sequential loop over the order positions [k0, k1): what utils.py:310-339 does, one candidate at a time, by ONE CTA
+// (any block size).  Used for small region counts and for the rare candidate whose neighbour set does not fit the
+// per-CTA table of the multi-CTA kernel below.
+__device__ void merge_serial_range(const MergeArgs& a, uint32_t k0, uint32_t k1) {
   __shared__ uint32_t s_first;
   __shared__ Box s_box;
   __shared__ uint32_t s_ntouched;
@@ -466,14 +473,13 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
   const int tid = threadIdx.x;
   const Dim d = a.d;
   const size_t HW = (size_t)d.H * d.W;
-  const uint32_t R = *a.d_R < a.cap ? *a.d_R : a.cap;
-  uint32_t k = 0;
-  while (k < R) {
+  uint32_t k = k0;
+  while (k < k1) {
     // The tables only change when a candidate is processed, so the next candidate can be searched for
-    // 1024 regions at a time; the first hit (in list order) is the one the sequential loop would take.
+    // blockDim regions at a time; the first hit (in list order) is the one the sequential loop would take.
     if (tid == 0) s_first = NONE;
     __syncthreads();
-    if (k + tid < R) {
+    if (k + tid < k1) {
       const uint32_t rr = a.order[k + tid];
       const uint32_t ar = a.area[rr];
       const uint8_t v = a.value[rr];
@@ -540,6 +546,264 @@ __global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
       __threadfence();
     }
     __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) merge_loop_kernel(MergeArgs a) {
+  const uint32_t R = *a.d_R < a.cap ? *a.d_R : a.cap;
+  merge_serial_range(a, 0, R);
+}
+
+// ---- Q4 on many CTAs ---------------------------------------------------------------------------------------------
+// The loop is sequential by definition (every merge changes the label map the next candidate sees), but candidates
+// whose extents are not even adjacent cannot see each other's merges: a merge of region i into its neighbour changes
+// (a) the ids of i's voxels, which only matter to a candidate j if they lie in j's ring - impossible when the boxes
+// of i and j are separated by a voxel - and (b) the target's area / record, which are applied in order afterwards.
+// So the kernel processes the order in BATCHES: the longest prefix of upcoming candidates whose extents are pairwise
+// separated (and that is not interrupted by a region a record growth could turn into a candidate).
+//   build (CTA 0)    classify a window of the order with the current tables, list the candidates in order, cut at the
+//                    first one that touches an earlier one
+//   decide (all)     one CTA per batch member: ring histogram in a shared-memory table, max count / lowest id -> target
+//   apply (CTA 0)    the area / record arithmetic of utils.py:333-339 sequentially in order on shared-memory copies
+//                    (tens of cycles per member), then cur / bbox / area / record written back in parallel; a merge that
+//                    lifts a skipped (< skip_below) region inside the batch's span over the threshold truncates the batch
+//                    there (that region becomes a candidate at its turn)
+// two grid-wide synchronisations per batch (cooperative launch).  tests: the CPU emulation of exactly this schedule
+// against the sequential loop (tests/test_merge_batches.py) and the bit-exact post-processing tests with either kernel.
+constexpr int MC_THREADS = 512;
+constexpr int MC_BMAX = 256;      // members per batch
+constexpr int MC_WINDOW = 2048;   // order positions classified per build step
+constexpr int MC_HASH = 1024;     // neighbour ids per candidate in the per-CTA table (more: the serial routine takes over)
+constexpr uint32_t MC_SMALL = 192;  // up to this many regions CTA 0 simply runs the sequential loop
+constexpr uint32_t MC_OVERFLOW = 0xFFFFFFFEu;
+// global scratch (uint32): [0] k  [1] members  [2] end  [3] serial flag  [4] done ; then region / position / target per member
+constexpr int MC_CTL = 8, MC_REGION = MC_CTL, MC_POS = MC_REGION + MC_BMAX, MC_TARGET = MC_POS + MC_BMAX, MC_WORDS = MC_TARGET + MC_BMAX;
+
+__device__ __forceinline__ bool boxes_separated(const int* p, const int* q) {   // a voxel of gap along some axis
+  return p[0] >= q[1] + 1 || q[0] >= p[1] + 1 || p[2] >= q[3] + 1 || q[2] >= p[3] + 1 || p[4] >= q[5] + 1 || q[4] >= p[5] + 1;
+}
+
+// apply the previous batch (if any), then build the next one; CTA 0 only
+__device__ void mc_apply_and_build(const MergeArgs& a, const uint32_t* pos_of, uint32_t* mc, uint32_t R) {
+  __shared__ uint8_t s_cls[MC_WINDOW];
+  __shared__ uint32_t s_list[MC_BMAX];
+  __shared__ int s_box[MC_BMAX][6];
+  __shared__ uint32_t s_r[MC_BMAX], s_pos[MC_BMAX], s_t[MC_BMAX], s_ar[MC_BMAX], s_at[MC_BMAX], s_pt[MC_BMAX], s_slot[MC_BMAX];
+  __shared__ uint8_t s_tv[MC_BMAX], s_applied[MC_BMAX];
+  __shared__ uint32_t s_rec[256];
+  __shared__ uint32_t s_k, s_a, s_b, s_n, s_warp[MC_THREADS / 32];
+  const int tid = threadIdx.x;
+  const uint32_t skip = (uint32_t)a.skip_below;
+
+  // ---------------- apply
+  const uint32_t n = mc[1], end = mc[2];
+  if (tid == 0) s_k = mc[0];
+  if (n > 0) {
+    if (tid < (int)n) {
+      const uint32_t r = mc[MC_REGION + tid], t = mc[MC_TARGET + tid];
+      s_r[tid] = r; s_pos[tid] = mc[MC_POS + tid]; s_t[tid] = t; s_ar[tid] = a.area[r]; s_applied[tid] = 0;
+      if (t != MC_OVERFLOW && t != r) { s_tv[tid] = a.value[t]; s_at[tid] = a.area[t]; s_pt[tid] = pos_of[t]; }
+    }
+    for (int i = tid; i < 256; i += blockDim.x) s_rec[i] = a.record[i];
+    __syncthreads();
+    if (tid < (int)n) {   // the first member with the same target carries that target's running area
+      uint32_t s = tid;
+      for (int m = 0; m < tid; ++m) if (s_t[m] == s_t[tid]) { s = m; break; }
+      s_slot[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t trunc = NONE, serial = 0;
+      for (uint32_t m = 0; m < n; ++m) {
+        if (trunc != NONE && s_pos[m] > trunc) break;
+        const uint32_t t = s_t[m];
+        if (t == MC_OVERFLOW) { trunc = s_pos[m]; serial = 1; break; }   // too many neighbours for the table: sequential routine
+        s_applied[m] = 1;
+        if (t == s_r[m]) continue;                       // no eligible neighbour: moved = 0, nothing changes (utils.py:330-339)
+        const uint32_t s = s_slot[m], before = s_at[s], moved = s_ar[m];
+        if (before == s_rec[s_tv[m]]) s_rec[s_tv[m]] += moved;   // utils.py:336-337
+        s_at[s] = before + moved;                                   // utils.py:339
+        // a skipped region inside the span grew over the threshold: it is a candidate when its turn comes
+        if (before < skip && before + moved >= skip && s_pt[m] > s_pos[m] && s_pt[m] < end && s_pt[m] < trunc) trunc = s_pt[m];
+      }
+      s_k = (trunc != NONE) ? trunc : end;
+      mc[3] = serial;
+    }
+    __syncthreads();
+    if (tid < (int)n && s_applied[tid] && s_t[tid] != s_r[tid]) {
+      const uint32_t r = s_r[tid], t = s_t[tid];
+      a.cur[r] = t;                                      // regionmask[regionmask == r] = t
+      int* bt = a.bbox + 6 * (size_t)t;
+      const int* br = a.bbox + 6 * (size_t)r;
+      atomicMin(&bt[0], br[0]); atomicMax(&bt[1], br[1]);
+      atomicMin(&bt[2], br[2]); atomicMax(&bt[3], br[3]);
+      atomicMin(&bt[4], br[4]); atomicMax(&bt[5], br[5]);
+      if (s_slot[tid] == (uint32_t)tid) a.area[t] = s_at[tid];
+    }
+    for (int i = tid; i < 256; i += blockDim.x) a.record[i] = s_rec[i];
+    __threadfence();
+    __syncthreads();
+  }
+
+  // ---------------- a member the table could not hold: the sequential routine processes exactly that position
+  if (mc[3]) {
+    const uint32_t k = s_k;
+    __syncthreads();
+    merge_serial_range(a, k, k + 1);
+    if (tid == 0) { s_k = k + 1; mc[3] = 0; }
+    __syncthreads();
+  }
+
+  // ---------------- build
+  while (true) {
+    const uint32_t k = s_k;
+    __syncthreads();
+    if (k >= R) { if (tid == 0) { mc[0] = R; mc[1] = 0; mc[4] = 1; } return; }
+    const uint32_t W = R - k < (uint32_t)MC_WINDOW ? R - k : (uint32_t)MC_WINDOW;
+    if (tid == 0) { s_a = NONE; s_b = NONE; s_n = 0; }
+    __syncthreads();
+    for (uint32_t p = tid; p < W; p += blockDim.x) {
+      const uint32_t rr = a.order[k + p];
+      const uint32_t ar = a.area[rr];
+      const uint8_t v = a.value[rr];
+      const bool cand = (ar < a.record[v] || a.spare_value[v]) && ar >= skip;
+      s_cls[p] = cand ? 1 : (ar >= skip ? 2 : 0);   // 2: a non-candidate that a record growth could turn into one
+      if (cand) atomicMin(&s_a, p);
+    }
+    __syncthreads();
+    const uint32_t first = s_a;
+    if (first == NONE) {   // nobody in the window is a candidate at its turn (nothing changes while we skip them)
+      if (tid == 0) s_k = k + W;
+      __syncthreads();
+      continue;
+    }
+    for (uint32_t p = tid; p < W; p += blockDim.x) if (p > first && s_cls[p] == 2) atomicMin(&s_b, p);
+    __syncthreads();
+    const uint32_t stop = s_b < W ? s_b : W;
+    // the candidates of [first, stop) in order: every thread owns a contiguous strip of the window
+    const uint32_t per = (uint32_t)MC_WINDOW / blockDim.x;
+    uint32_t cnt = 0;
+    for (uint32_t q = 0; q < per; ++q) { const uint32_t p = tid * per + q; cnt += (p >= first && p < stop && s_cls[p] == 1) ? 1u : 0u; }
+    uint32_t inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += v; }
+    if ((tid & 31) == 31) s_warp[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t w = tid < (int)(blockDim.x >> 5) ? s_warp[tid] : 0;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, w, o); if (tid >= o) w += v; }
+      if (tid < (int)(blockDim.x >> 5)) s_warp[tid] = w;
+    }
+    __syncthreads();
+    uint32_t off = inc - cnt + ((tid >> 5) ? s_warp[(tid >> 5) - 1] : 0);
+    const uint32_t total = s_warp[(blockDim.x >> 5) - 1];
+    for (uint32_t q = 0; q < per; ++q) {
+      const uint32_t p = tid * per + q;
+      if (p >= first && p < stop && s_cls[p] == 1) { if (off <= (uint32_t)MC_BMAX) { if (off < (uint32_t)MC_BMAX) s_list[off] = p; else s_n = p; } ++off; }
+    }
+    __syncthreads();
+    uint32_t nl = total < (uint32_t)MC_BMAX ? total : (uint32_t)MC_BMAX;
+    uint32_t endp = total > (uint32_t)MC_BMAX ? s_n : stop;   // the batch ends before the first candidate that did not fit
+    if (tid < (int)nl) {
+      const int* bb = a.bbox + 6 * (size_t)a.order[k + s_list[tid]];
+      for (int c = 0; c < 6; ++c) s_box[tid][c] = bb[c];
+    }
+    if (tid == 0) s_a = NONE;
+    __syncthreads();
+    if (tid < (int)nl) {
+      bool hit = false;
+      for (int i = 0; i < tid && !hit; ++i) hit = !boxes_separated(s_box[i], s_box[tid]);
+      if (hit) atomicMin(&s_a, (uint32_t)tid);
+    }
+    __syncthreads();
+    if (s_a != NONE) { nl = s_a; endp = s_list[s_a]; }   // cut before the first member that touches an earlier one (nl >= 1)
+    if (tid < (int)nl) { mc[MC_REGION + tid] = a.order[k + s_list[tid]]; mc[MC_POS + tid] = k + s_list[tid]; }
+    if (tid == 0) { mc[0] = k; mc[1] = nl; mc[2] = k + endp; mc[4] = 0; }
+    __threadfence();
+    __syncthreads();
+    return;
+  }
+}
+
+// one batch member: the target the sequential loop would pick for region r given the current tables
+__device__ void mc_decide(const MergeArgs& a, uint32_t* mc, uint32_t m) {
+  __shared__ uint32_t h_key[MC_HASH], h_cnt[MC_HASH];
+  __shared__ uint32_t s_over;
+  __shared__ unsigned long long s_best;
+  const int tid = threadIdx.x;
+  const Dim d = a.d;
+  const size_t HW = (size_t)d.H * d.W;
+  const uint32_t r = mc[MC_REGION + m];
+  for (int i = tid; i < MC_HASH; i += blockDim.x) { h_key[i] = 0; h_cnt[i] = 0; }
+  if (tid == 0) { s_over = 0; s_best = 0ull; }
+  __syncthreads();
+  Box b;
+  {
+    const int* bb = a.bbox + 6 * (size_t)r;
+    b.z0 = max(bb[0] - 1, 0); b.z1 = min(bb[1] + 1, d.S);
+    b.y0 = max(bb[2] - 1, 0); b.y1 = min(bb[3] + 1, d.H);
+    b.x0 = max(bb[4] - 1, 0); b.x1 = min(bb[5] + 1, d.W);
+  }
+  const size_t n = box_volume(b);
+  for (size_t t = tid; t < n; t += blockDim.x) {
+    int z, y, x;
+    const uint32_t i = box_voxel(b, d, t, z, y, x);
+    const uint32_t o = a.rid[i];
+    if (o == 0 || o > a.cap) continue;
+    const uint32_t id = cur_find(a.cur, o);
+    if (id == r) continue;
+    bool ring = false;
+    if (x > 0)       { const uint32_t q = a.rid[i - 1];   ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+    if (x < d.W - 1) { const uint32_t q = a.rid[i + 1];   ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+    if (y > 0)       { const uint32_t q = a.rid[i - d.W]; ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+    if (y < d.H - 1) { const uint32_t q = a.rid[i + d.W]; ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+    if (z > 0)       { const uint32_t q = a.rid[i - HW];  ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+    if (z < d.S - 1) { const uint32_t q = a.rid[i + HW];  ring |= (q && q <= a.cap && cur_find(a.cur, q) == r); }
+    if (!ring) continue;
+    uint32_t h = (id * 2654435761u) & (MC_HASH - 1);
+    int probes = 0;
+    while (true) {
+      const uint32_t old = atomicCAS(&h_key[h], 0u, id);
+      if (old == 0u || old == id) { atomicAdd(&h_cnt[h], 1u); break; }
+      h = (h + 1) & (MC_HASH - 1);
+      if (++probes >= MC_HASH) { s_over = 1; break; }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < MC_HASH; i += blockDim.x) {
+    const uint32_t id = h_key[i];
+    if (id == 0 || a.spare_id[id]) continue;
+    atomicMax(&s_best, ((unsigned long long)h_cnt[i] << 32) | (unsigned long long)(0xFFFFFFFFu - id));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t target = r;
+    if (s_over) target = MC_OVERFLOW;
+    else if (s_best != 0ull) target = 0xFFFFFFFFu - (uint32_t)(s_best & 0xFFFFFFFFull);
+    mc[MC_TARGET + m] = target;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(MC_THREADS, 1) merge_loop_mc_kernel(MergeArgs a, uint32_t* pos_of, uint32_t* mc) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t R = *a.d_R < a.cap ? *a.d_R : a.cap;
+  if (R <= MC_SMALL || gridDim.x == 1) {   // (uniform over the grid: nobody reaches a grid-wide synchronisation)
+    if (blockIdx.x == 0) merge_serial_range(a, 0, R);
+    return;
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) pos_of[a.order[i]] = i;
+  if (blockIdx.x == 0 && threadIdx.x < MC_CTL) mc[threadIdx.x] = 0;
+  __threadfence();
+  grid.sync();
+  while (true) {
+    if (blockIdx.x == 0) mc_apply_and_build(a, pos_of, mc, R);
+    __threadfence();
+    grid.sync();
+    if (mc[4]) break;
+    const uint32_t n = mc[1];
+    for (uint32_t m = blockIdx.x; m < n; m += gridDim.x) mc_decide(a, mc, m);
+    __threadfence();
+    grid.sync();
   }
 }
 
@@ -785,9 +1049,9 @@ int PostScratch::reserve(size_t nvox) {
 void PostScratch::release_regions() {
   cudaFree(r_area); cudaFree(r_value); cudaFree(r_bbox); cudaFree(r_cur); cudaFree(r_order); cudaFree(r_count);
   cudaFree(r_touched); cudaFree(r_spare_id); cudaFree(r_to_label); cudaFree(r_hslot); cudaFree(sort_keys);
-  cudaFree(hash_keys); cudaFree(hash_min); cudaFree(batch);
+  cudaFree(hash_keys); cudaFree(hash_min); cudaFree(batch); cudaFree(r_pos);
   r_area = r_cur = r_order = r_count = r_touched = r_hslot = nullptr; r_value = r_spare_id = r_to_label = nullptr; r_bbox = nullptr;
-  sort_keys = hash_keys = nullptr; hash_min = nullptr; batch = nullptr;
+  sort_keys = hash_keys = nullptr; hash_min = nullptr; batch = nullptr; r_pos = nullptr;
   cap_regions = 0; hash_cap = 0; sort_cap = 0;
 }
 int PostScratch::reserve_regions(uint32_t R) {
@@ -800,6 +1064,7 @@ int PostScratch::reserve_regions(uint32_t R) {
   A(&r_area, c * 4); A(&r_value, c); A(&r_bbox, c * 6 * 4); A(&r_cur, c * 4); A(&r_order, c * 4); A(&r_count, c * 4);
   A(&r_touched, c * 4); A(&r_spare_id, c); A(&r_to_label, c); A(&r_hslot, c * 4);
   A(&sort_keys, (size_t)sc * 8); A(&hash_keys, (size_t)hc * 8); A(&hash_min, (size_t)hc * 4);
+  A(&r_pos, c * 4); A(&batch, (size_t)MC_WORDS * 4);
   if (rc) { release_regions(); return rc; }
   cap_regions = R; hash_cap = hc; sort_cap = sc;
   return 0;
@@ -870,7 +1135,26 @@ int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, i
   ma.record = d_record; ma.order = ws.r_order; ma.count = ws.r_count; ma.touched = ws.r_touched;
   ma.spare_value = d_spare_value; ma.spare_id = ws.r_spare_id; ma.d_R = d_small + W_R; ma.cap = cap;
   ma.skip_below = skip_below; ma.d = d;
-  merge_loop_kernel<<<1, 1024, 0, st>>>(ma);
+  // many CTAs when the device can co-schedule a grid (cooperative launch), else the one-CTA loop
+  bool launched = false;
+  if (ws.merge_ctas != 1) {
+    static std::atomic<int> coop_ok{-1};   // -1 unknown, 0 no, 1 yes (per process: every engine device is a B200)
+    if (coop_ok.load() < 0) {
+      int dev = 0, v = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess) coop_ok.store(v ? 1 : 0);
+      else coop_ok.store(0);
+    }
+    if (coop_ok.load() == 1) {
+      uint32_t* pos_of = ws.r_pos;
+      uint32_t* mc = ws.batch;
+      void* args[] = {(void*)&ma, (void*)&pos_of, (void*)&mc};
+      const int ctas = ws.merge_ctas > 1 ? (ws.merge_ctas < num_sms ? ws.merge_ctas : num_sms) : num_sms;
+      const cudaError_t ce = cudaLaunchCooperativeKernel((void*)merge_loop_mc_kernel, dim3(ctas), dim3(MC_THREADS), args, 0, st);
+      if (ce == cudaSuccess) launched = true;
+      else { cudaGetLastError(); coop_ok.store(0); }
+    }
+  }
+  if (!launched) merge_loop_kernel<<<1, 1024, 0, st>>>(ma);
   // Q5
   map_labels_kernel<<<g, 256, 0, st>>>(ws.rid, ws.r_cur, ws.r_to_label, d_spare_value, ws.mapped, n, d_present, cap);
   *launches += 11;

@@ -16,7 +16,8 @@ struct PostScratch {
   uint32_t last_regions = 0;  // largest region count seen since the previous postprocess_finish
   bool clear_sticky = true;   // the next run resets the device's sticky overflow flag / region-count maximum
   int ccl_rule = 1;           // 26-connected union-find: 1 = pruned neighbour rule (default), 0 = all 13 backward probes
-  int merge_ctas = 0;         // merge loop: 0 = auto (cooperative multi-CTA when supported), 1 = the single-CTA loop
+  int merge_ctas = 0;         // merge loop: 0 = one CTA per SM in batches of independent candidates (cooperative launch),
+                              // 1 = the single-CTA sequential loop, n > 1 = that many CTAs
   int debug_stage = 0;        // parity taps: 1 = return the Q5 label map, 2 = region ids & 255, 3 = merged ids & 255
   uint32_t *parent = nullptr, *parent2 = nullptr, *rid = nullptr, *area2 = nullptr;
   uint8_t *mapped = nullptr, *tmp = nullptr, *outside = nullptr;
@@ -28,7 +29,8 @@ struct PostScratch {
   int* r_bbox = nullptr;
   uint64_t *sort_keys = nullptr, *hash_keys = nullptr;
   uint32_t* hash_min = nullptr;
-  uint32_t* batch = nullptr;    // multi-CTA merge loop: per-batch candidate tables
+  uint32_t* batch = nullptr;    // multi-CTA merge loop: control words + per-batch member tables
+  uint32_t* r_pos = nullptr;    // multi-CTA merge loop: position of every region in the (area, id) order
   int reserve(size_t nvox);
   int reserve_regions(uint32_t R);
   void release();

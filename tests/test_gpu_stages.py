@@ -145,3 +145,22 @@ def test_sort_paths(engine):
     big = rng.integers(0, 5, size=(6, 64, 64)).astype(np.uint8)         # > 4096 regions
     for lab in (small, big):
         assert np.array_equal(engine.postprocess(lab), restate.postprocessing(lab))
+
+
+def test_merge_kernels_agree(engine):
+    """Q4 on one CTA (lm_set_option("merge_ctas", 1)) and on one CTA per SM in batches of independent candidates
+    (default): the same post-processing, bit for bit, and both equal the oracle - thousands of regions, spare labels,
+    skip_below = 1 (every speckle is a candidate)."""
+    rng = np.random.default_rng(21)
+    vols = [synth.label_noise_volume(16, 3, seed=31, speckle=2e-2),                   # lungs + dense speckle
+            synth.label_noise_volume(10, 6, seed=32, speckle=5e-3, H=200, W=312),
+            rng.integers(0, 4, size=(6, 48, 48)).astype(np.uint8)]                     # pure noise
+    for lab in vols:
+        for kw in ({}, {"spare": [int(lab.max())]}, {"skip_below": 1}):
+            want = restate.postprocessing(lab, **kw)
+            assert np.array_equal(engine.postprocess(lab, **kw), want), kw
+            engine.set_option("merge_ctas", 1)
+            try:
+                assert np.array_equal(engine.postprocess(lab, **kw), want), kw
+            finally:
+                engine.set_option("merge_ctas", 0)
