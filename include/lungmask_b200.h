@@ -109,7 +109,9 @@ LM_API int lm_apply_volume_oriented(lm_engine* e, int slot, int slot_fill, const
  * slice range [r * ceil(S/world), (r+1) * ceil(S/world)) and the uint8 argmax volume (plus the crop boxes) is
  * all-gathered once - by the engine itself: every rank owns a gather block in device memory that its peers map through
  * CUDA IPC, a rank pushes its slab into every peer's block over NVLink and raises an epoch flag there; post-processing
- * and reshape then run replicated on the gathered volume and every rank holds the whole result.
+ * and reshape then run replicated on the gathered volume and every rank holds the whole result.  The 3-D labelling of
+ * utils.py:293 is slab-sharded too: every rank labels its own slices, the union-find parents travel with the labels,
+ * and after the gather only the slab boundaries are linked ("shard_slab_ccl", default 1).
  *   lm_shard_init     allocates this rank's gather block for volumes of up to max_slices slices
  *   lm_shard_export   writes the block's IPC handle (lm_shard_handle_bytes() bytes) - exchange it by any host channel
  *   lm_shard_connect  maps the peers' blocks; `handles` = world handles in rank order (this rank's own is ignored)

@@ -162,6 +162,9 @@ struct lm_engine {
   void* act[NUM_ACT] = {};  // split buffers: op_t planes; "L" buffers: fp32
   ShardView shard;             // multi-GPU slice sharding (lm_shard_*): gather blocks of all ranks
   bool shard_connected = false;
+  int shard_test_slabs = 0;    // test hook (world == 1): label that many virtual slabs separately and join them
+  int shard_slab_ccl = 1;      // 1: every rank labels its own slab, parents travel with the labels, boundaries are joined after
+                               // the gather; 0: every rank labels the whole gathered volume
   uint32_t shard_epoch = 0;
   uint32_t* h_shard_err = nullptr;  // pinned copy of the block's error word
   int32_t* d_spare = nullptr;  // device int32[16]: spare label values computed on the device (fusion, mask.py:228)
@@ -516,16 +519,45 @@ int sharded_dev(lm_engine* e, int slot, const int16_t* d_vol, int S, int H, int 
   CU(cudaEventRecord(e->ev[2], e->st));
   if (ns > 0) RC(forward_all(e, slot, e->d_resized.p, ns, labels_full + (size_t)lo * rr, nullptr, nullptr));
   CU(cudaEventRecord(e->ev[3], e->st));
+  // slab-sharded 3-D labelling: this rank labels its own slices (26-connected, neighbours outside the slab
+  // ignored) and ships the union-find parents with the labels; after the gather every rank only links the slab
+  // boundaries and flattens
+  const bool want_post = !(flags & LM_FLAG_NO_POSTPROCESS);
+  const bool slab_ccl = want_post && e->shard_slab_ccl;
+  uint32_t* parents_full = reinterpret_cast<uint32_t*>(v.block[v.rank] + shard_parents_offset(v.slice_cap, rr));
+  const int vworld = (v.world == 1 && e->shard_test_slabs > 1) ? e->shard_test_slabs : v.world;   // test hook: virtual slabs on one GPU
+  if (slab_ccl) {
+    if (vworld == v.world) {
+      if (ns > 0) RC(ccl_slab_device(labels_full, parents_full, S, R, R, lo, hi, e->post.ccl_rule, e->num_sms, e->st, &e->launches));
+    } else {
+      for (int r2 = 0; r2 < vworld; ++r2) {
+        int l2, h2;
+        shard_range(S, r2, vworld, &l2, &h2);
+        RC(ccl_slab_device(labels_full, parents_full, S, R, R, l2, h2, e->post.ccl_rule, e->num_sms, e->st, &e->launches));
+      }
+    }
+  }
   // the collective: wait until the peers have consumed the previous volume, push the slab, wait for theirs
   RC(launch_shard_wait_done(v, epoch, e->st));
-  RC(launch_shard_push(v, (size_t)lo, (size_t)hi, rr, epoch, e->num_sms, e->st));
+  RC(launch_shard_push(v, (size_t)lo, (size_t)hi, rr, slab_ccl, epoch, e->num_sms, e->st));
   RC(launch_shard_wait_ready(v, epoch, e->st));
   e->launches += v.world > 1 ? 3 : 0;
   const uint8_t* masks = labels_full;
-  if (!(flags & LM_FLAG_NO_POSTPROCESS)) {
+  if (want_post) {
     RC(e->d_post.reserve((size_t)S * rr));
+    uint32_t* parent_in = nullptr;
+    if (slab_ccl) {
+      int firsts[kShardMaxWorld], nbounds = 0;
+      for (int r2 = 1; r2 < vworld; ++r2) {
+        int l2, h2;
+        shard_range(S, r2, vworld, &l2, &h2);
+        if (h2 > l2) firsts[nbounds++] = l2;
+      }
+      RC(ccl_join_slabs_device(labels_full, parents_full, S, R, R, firsts, nbounds, e->num_sms, e->st, &e->launches));
+      parent_in = parents_full;
+    }
     RC(postprocess_device(e->post, labels_full, S, R, R, nullptr, 0, nullptr, 0, 3, e->slots[slot].K - 1, e->d_post.p, e->num_sms, e->st,
-                          &e->launches));
+                          &e->launches, parent_in));
     masks = e->d_post.p;
   }
   CU(cudaEventRecord(e->ev[4], e->st));
@@ -1195,6 +1227,8 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
   if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value != 0; return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
+  if (!strcmp(key, "shard_slab_ccl")) { e->shard_slab_ccl = value != 0; return 0; }
+  if (!strcmp(key, "shard_test_slabs")) { if (value < 0 || value > kShardMaxWorld) return fail(-1, "shard_test_slabs out of range"); e->shard_test_slabs = value; return 0; }
   if (!strcmp(key, "merge_ctas")) { if (value < 0) return fail(-1, "merge_ctas must be >= 0"); e->post.merge_ctas = value; return 0; }
   if (!strcmp(key, "post_region_capacity")) {  // test hook: shrink / grow the region tables (exercises the overflow re-run)
     if (value < 1) return fail(-1, "post_region_capacity must be >= 1");

@@ -172,6 +172,33 @@ __global__ void ccl_merge_kernel(const uint8_t* __restrict__ vals, uint32_t* __r
   }
 }
 
+// Joins slab-wise labellings (multi-GPU slice sharding, shard.cu): every slab [z_lo, z_hi) was labelled on its own
+// with neighbours outside the slab ignored; here the voxels of each slab's FIRST slice are united with their nine
+// backward neighbours in the previous slab's last slice.  Roots stay minimum linear indices, so the union of slab
+// labellings plus these links is exactly the whole-volume labelling.  bounds: the first slices of slabs 1..n-1.
+struct SlabBounds { int n; int z[16]; };
+__global__ void ccl_join_slabs_kernel(const uint8_t* __restrict__ vals, uint32_t* __restrict__ parent, Dim d, SlabBounds sb) {
+  const size_t HW = (size_t)d.H * d.W;
+  const size_t total = (size_t)sb.n * HW;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int z = sb.z[t / HW];
+    const size_t r = t % HW;
+    const int y = (int)(r / d.W), x = (int)(r % d.W);
+    const uint32_t i = (uint32_t)((size_t)z * HW + r);
+    const uint8_t v = vals[i];
+    if (!v || z == 0) continue;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = y + dy, xx = x + dx;
+        if (yy < 0 || yy >= d.H || xx < 0 || xx >= d.W) continue;
+        const uint32_t j = (uint32_t)((size_t)(z - 1) * HW + (size_t)yy * d.W + xx);
+        if (vals[j] == v) uf_union(parent, i, j);
+      }
+  }
+}
+
 // Read-only walk: while flattening, a thread may only write its OWN slot; a path-halving write from another
 // walker could overwrite an already flattened slot with a stale non-root ancestor.
 __device__ __forceinline__ uint32_t uf_find_ro(const uint32_t* parent, uint32_t i) {
@@ -1078,9 +1105,40 @@ void PostScratch::release() {
   cap_vox = 0;
 }
 
+int ccl_slab_device(const uint8_t* d_labels, uint32_t* d_parent, int S, int H, int W, int z_lo, int z_hi, int rule, int num_sms,
+                    cudaStream_t st, int64_t* launches) {
+  if (z_hi <= z_lo) return 0;
+  const Dim d{S, H, W};
+  const Box slab{z_lo, z_hi, 0, H, 0, W};
+  const BoxSrc bs = fixed_box(slab);
+  const size_t n = (size_t)(z_hi - z_lo) * H * W;
+  const int g = grid_for(n, 256, num_sms);
+  ccl_init_kernel<<<g, 256, 0, st>>>(d_labels, d_parent, d, bs);
+  ccl_merge_kernel<26><<<g, 256, 0, st>>>(d_labels, d_parent, d, bs, rule);
+  *launches += 2;
+  return (int)cudaGetLastError();
+}
+
+int ccl_join_slabs_device(const uint8_t* d_labels, uint32_t* d_parent, int S, int H, int W, const int* first_slices, int n_bounds,
+                          int num_sms, cudaStream_t st, int64_t* launches) {
+  const Dim d{S, H, W};
+  const Box full{0, S, 0, H, 0, W};
+  if (n_bounds > 16) return -24;
+  if (n_bounds > 0) {
+    SlabBounds sb{};
+    sb.n = n_bounds;
+    for (int i = 0; i < n_bounds; ++i) sb.z[i] = first_slices[i];
+    ccl_join_slabs_kernel<<<grid_for((size_t)n_bounds * H * W, 256, num_sms), 256, 0, st>>>(d_labels, d_parent, d, sb);
+    *launches += 1;
+  }
+  ccl_flatten_kernel<<<grid_for((size_t)S * H * W, 256, num_sms), 256, 0, st>>>(d_parent, d, fixed_box(full));
+  *launches += 1;
+  return (int)cudaGetLastError();
+}
+
 int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, int W, const int32_t* spare, int n_spare,
                        const int32_t* d_spare, int n_d_spare, int skip_below, int max_label, uint8_t* d_out, int num_sms,
-                       cudaStream_t st, int64_t* launches) {
+                       cudaStream_t st, int64_t* launches, uint32_t* parent_in) {
   const size_t n = (size_t)S * H * W;
   if (n == 0) return 0;
   if (n >= 0xFFFFFFF0ull) return -20;
@@ -1109,19 +1167,23 @@ int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, i
   post_setup_kernel<<<1, 256, 0, st>>>(d_small, sp, ws.clear_sticky ? 1 : 0);
   ws.clear_sticky = false;
 
-  // Q1: components + canonical ids (R stays on the device: d_small[W_R])
-  rc = run_ccl<26>(d_labels, ws.parent, d, fullsrc, n, num_sms, st, launches, ws.ccl_rule);
-  if (rc) return rc;
+  // Q1: components + canonical ids (R stays on the device: d_small[W_R]); parent_in: the flattened union-find of a
+  // slab-wise labelling that the caller has already joined (ccl_slab_device / ccl_join_slabs_device)
+  uint32_t* const parent1 = parent_in ? parent_in : ws.parent;
+  if (!parent_in) {
+    rc = run_ccl<26>(d_labels, ws.parent, d, fullsrc, n, num_sms, st, launches, ws.ccl_rule);
+    if (rc) return rc;
+  }
   const int nb = (int)((n + SCAN_BLOCK * SCAN_ITEMS - 1) / (SCAN_BLOCK * SCAN_ITEMS));
-  roots_count_kernel<<<nb, SCAN_BLOCK, 0, st>>>(ws.parent, n, ws.block_counts);
+  roots_count_kernel<<<nb, SCAN_BLOCK, 0, st>>>(parent1, n, ws.block_counts);
   scan_blocks_kernel<<<1, 1024, 0, st>>>(ws.block_counts, nb, d_small + W_R);
-  roots_assign_kernel<<<nb, SCAN_BLOCK, 0, st>>>(ws.parent, n, ws.block_counts, ws.rid);
+  roots_assign_kernel<<<nb, SCAN_BLOCK, 0, st>>>(parent1, n, ws.block_counts, ws.rid);
 
   // Q2: region tables
   const int gr = grid_for((size_t)cap + 1, 256, num_sms);
   region_init_kernel<<<gr, 256, 0, st>>>(d_small, cap, ws.r_area, ws.r_count, ws.r_value, ws.r_bbox, ws.r_cur, ws.r_to_label,
                                          ws.r_spare_id);
-  region_stats_kernel<<<g, 256, 0, st>>>(d_labels, ws.parent, ws.rid, d, cap, ws.r_area, ws.r_value, ws.r_bbox);
+  region_stats_kernel<<<g, 256, 0, st>>>(d_labels, parent1, ws.rid, d, cap, ws.r_area, ws.r_value, ws.r_bbox);
   // Q3: ascending (area, id) order, per-label records, region -> label table
   region_sort_kernel<<<1, 1024, 0, st>>>(d_small, cap, ws.r_area, reinterpret_cast<unsigned long long*>(ws.sort_keys), ws.r_order);
   LM_CUDA(cudaMemsetAsync(ws.hash_keys, 0xFF, (size_t)ws.hash_cap * 8, st));

@@ -45,8 +45,16 @@ struct PostScratch {
 // overflowed (ws.want_regions is set; reserve_regions(want_regions) and run again - the output is invalid).
 int postprocess_device(PostScratch& ws, const uint8_t* d_labels, int S, int H, int W, const int32_t* spare, int n_spare,
                        const int32_t* d_spare, int n_d_spare, int skip_below, int max_label, uint8_t* d_out, int num_sms,
-                       cudaStream_t st, int64_t* launches);
+                       cudaStream_t st, int64_t* launches, uint32_t* parent_in = nullptr);
 int postprocess_finish(PostScratch& ws);
+// Slab-wise 3-D labelling (multi-GPU slice sharding): ccl_slab_device labels the slices [z_lo, z_hi) of the (S,H,W) label
+// volume on their own into d_parent (global linear indices, neighbours outside the slab ignored; not flattened);
+// ccl_join_slabs_device links every slab's first slice (first_slices[0..n_bounds)) to the previous slab and flattens the
+// whole volume - the result equals the whole-volume labelling and is what postprocess_device takes as parent_in.
+int ccl_slab_device(const uint8_t* d_labels, uint32_t* d_parent, int S, int H, int W, int z_lo, int z_hi, int rule, int num_sms,
+                    cudaStream_t st, int64_t* launches);
+int ccl_join_slabs_device(const uint8_t* d_labels, uint32_t* d_parent, int S, int H, int W, const int* first_slices, int n_bounds,
+                          int num_sms, cudaStream_t st, int64_t* launches);
 // utils.keep_largest_connected_component on a device-resident (S,H,W) 0/1 mask; -21 if the mask is empty.
 int keep_largest_component_device(PostScratch& ws, const uint8_t* d_mask, int S, int H, int W, uint8_t* d_out, int num_sms,
                                   cudaStream_t st);

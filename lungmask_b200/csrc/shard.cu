@@ -40,21 +40,19 @@ __global__ void shard_wait_kernel(uint32_t* own, int word0, int world, uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(256) shard_push_kernel(Blocks bl, int rank, int world, size_t box_off, size_t box_bytes,
-                                                         size_t lab_off, size_t lab_bytes, uint32_t epoch) {
-  // both ranges are multiples of 16 bytes at 16-byte aligned offsets (boxes: 16 B per slice, labels: 64 KB per slice)
-  const uint4* src_box = reinterpret_cast<const uint4*>(bl.b[rank] + box_off);
-  const uint4* src_lab = reinterpret_cast<const uint4*>(bl.b[rank] + lab_off);
-  const size_t nb = box_bytes / 16, nl = lab_bytes / 16;
+struct Ranges { size_t off[3]; size_t n16[3]; };   // byte offsets in the block and lengths in 16-byte units
+
+__global__ void __launch_bounds__(256) shard_push_kernel(Blocks bl, int rank, int world, Ranges rg, uint32_t epoch) {
+  // every range is a multiple of 16 bytes at a 16-byte aligned offset (boxes: 16 B, labels: 64 KB, parents: 256 KB per slice)
+  const size_t total = rg.n16[0] + rg.n16[1] + rg.n16[2];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nl + nb; i += stride) {
-    const bool is_box = i >= nl;
-    const size_t k = is_box ? i - nl : i;
-    const uint4 v = is_box ? src_box[k] : src_lab[k];
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int r = i < rg.n16[0] ? 0 : (i < rg.n16[0] + rg.n16[1] ? 1 : 2);
+    const size_t k = i - (r > 0 ? rg.n16[0] : 0) - (r > 1 ? rg.n16[1] : 0);
+    const uint4 v = reinterpret_cast<const uint4*>(bl.b[rank] + rg.off[r])[k];
     for (int p = 1; p < world; ++p) {           // start with the next rank: the ranks' stores spread over the switch
       const int peer = (rank + p) % world;
-      uint4* dst = reinterpret_cast<uint4*>(bl.b[peer] + (is_box ? box_off : lab_off)) + k;
-      *dst = v;
+      reinterpret_cast<uint4*>(bl.b[peer] + rg.off[r])[k] = v;
     }
   }
   // the last block to finish publishes the flag: every other block's stores precede its ticket (fence + atomic)
@@ -94,16 +92,19 @@ int launch_shard_wait_done(const ShardView& v, uint32_t epoch, cudaStream_t st) 
   return (int)cudaGetLastError();
 }
 
-int launch_shard_push(const ShardView& v, size_t lo, size_t hi, size_t label_bytes_per_slice, uint32_t epoch, int num_sms,
-                      cudaStream_t st) {
+int launch_shard_push(const ShardView& v, size_t lo, size_t hi, size_t label_bytes_per_slice, bool with_parents, uint32_t epoch,
+                      int num_sms, cudaStream_t st) {
   if (v.world <= 1) return 0;
-  const size_t box_off = shard_boxes_offset() + lo * 16, box_bytes = (hi - lo) * 16;
-  const size_t lab_off = shard_labels_offset(v.slice_cap) + lo * label_bytes_per_slice, lab_bytes = (hi - lo) * label_bytes_per_slice;
-  size_t blocks = (lab_bytes / 16 + box_bytes / 16 + 255) / 256;
+  Ranges rg{};
+  rg.off[0] = shard_boxes_offset() + lo * 16; rg.n16[0] = (hi - lo);
+  rg.off[1] = shard_labels_offset(v.slice_cap) + lo * label_bytes_per_slice; rg.n16[1] = (hi - lo) * label_bytes_per_slice / 16;
+  rg.off[2] = shard_parents_offset(v.slice_cap, label_bytes_per_slice) + lo * label_bytes_per_slice * 4;
+  rg.n16[2] = with_parents ? (hi - lo) * label_bytes_per_slice * 4 / 16 : 0;
+  size_t blocks = (rg.n16[0] + rg.n16[1] + rg.n16[2] + 255) / 256;
   const size_t cap = (size_t)num_sms * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;   // an empty slab still publishes its flag
-  shard_push_kernel<<<(int)blocks, 256, 0, st>>>(blocks_of(v), v.rank, v.world, box_off, box_bytes, lab_off, lab_bytes, epoch);
+  shard_push_kernel<<<(int)blocks, 256, 0, st>>>(blocks_of(v), v.rank, v.world, rg, epoch);
   return (int)cudaGetLastError();
 }
 
