@@ -190,7 +190,10 @@ def run_engine(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from lungmask_b200 import LMInferer
     from lungmask_b200 import parallel
+    from lungmask_b200.logger import logger as lm_logger
     from oracle import synth
+    import logging
+    lm_logger.setLevel(logging.WARNING)   # the reference logs "Apply: ..." to stdout; stdout carries the JSON line here
 
     cfg = CONFIGS[args.config]
     shard = args.mode == "shard"

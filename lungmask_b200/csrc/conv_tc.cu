@@ -210,18 +210,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   constexpr int HALVES = C::HALVES, EGROUPS = C::EGROUPS;
   constexpr int NC = BN / HALVES;  // accumulator columns held by one epilogue thread (64)
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + (EGROUPS + 1) * NBUF + 2 * NUM_A_BUFS];
-  __shared__ uint32_t tmem_base_s;
-  __shared__ float s_head_w[MAX_CLASSES * 64];
-  __shared__ float s_head_b[MAX_CLASSES];
+  extern __shared__ __align__(1024) uint8_t smem[];   // layout: Cfg<BN> (conv_tc_common.cuh); no static shared memory
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BARS);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+  float* s_head_w = reinterpret_cast<float*>(smem + C::OFF_HEAD);          // present for BN = 64 only (kModeHead)
+  float* s_head_b = s_head_w + MAX_CLASSES * 64;
 
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + EGROUPS * NBUF]);
   const uint32_t afull0 = smem_u32(&bars[2 * STAGES + (EGROUPS + 1) * NBUF]), aempty0 = afull0 + 8 * NUM_A_BUFS;
-  uint8_t* smem_b = smem + NUM_A_BUFS * A_BUF_BYTES;
-  uint8_t* smem_out = smem_b + STAGES * C::STAGE_BYTES;  // 2 x 16 KB, 1024-aligned
+  uint8_t* smem_b = smem + C::OFF_B;
+  uint8_t* smem_out = smem + C::OFF_STG;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int tiles_x = p.W / TILE_W, tiles_img = tiles_x * (p.H / TILE_H);
@@ -248,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmPool);
   }
   if (warp == 2) tmem_alloc(smem_u32(&tmem_base_s), C::TMEM_COLS);
-  if (p.mode == kModeHead) {
+  if (BN == 64 && p.mode == kModeHead) {
     for (int i = threadIdx.x; i < p.K * 64; i += NUM_THREADS) s_head_w[i] = p.head_w[i];
     if (threadIdx.x < p.K) s_head_b[threadIdx.x] = p.head_b[threadIdx.x];
   }
@@ -381,7 +380,7 @@ int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const voi
                    const ConvParams& p, int n_capacity) {
   const cuuint64_t E = kOpBytes;
   if (p.H % TILE_H || p.W % TILE_W || p.C0 % BK || p.C1 % BK || (p.taps != 1 && p.taps != 9)) return -2;
-  const int BN = conv_tile_n(p.Cout);
+  const int BN = conv_tile_n(p);
   if (p.Cout % BN) return -3;
   int r = make_act_map(&maps->a0, src0, n_capacity, p.H, p.W, p.C0, p.taps);
   if (r) return r;
@@ -463,8 +462,8 @@ int conv_tc_prepare() {
 int launch_conv_tc(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   if (p.mode == kModeHead && (p.Cout != 64 || p.K > MAX_CLASSES)) return -4;
   if (p.chunk_kb < 1) return -5;
-  return conv_tile_n(p.Cout) == 128 ? launch_impl<128>(maps, p, num_sms, stream)
-                                    : launch_impl<64>(maps, p, num_sms, stream);
+  return conv_tile_n(p) == 128 ? launch_impl<128>(maps, p, num_sms, stream)
+                               : launch_impl<64>(maps, p, num_sms, stream);
 }
 
 }  // namespace lm

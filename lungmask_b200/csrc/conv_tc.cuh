@@ -54,6 +54,8 @@ struct ConvParams {
   int chunk_kb;       // k-blocks (kBK channels x 1 tap) accumulated inside the tensor core before the
                       // partial sum is added, round-to-nearest, into fp32 registers
   int dual_issue;     // 1: two MMA-issuing threads take alternate chunks (0: one issuer)
+  int tile_n;         // output-channel tile: 0 = conv_tile_n(Cout); 64 forces the BN = 64 kernel (two epilogue groups on
+                      // alternate tiles) for a layer with Cout >= 128 - must be set before make_conv_maps
   const float* bias;  // [Cout]
   const float* scale; // [Cout]  folded BN:  y = relu(.) * scale + shift
   const float* shift; // [Cout]
@@ -98,5 +100,6 @@ int conv_tc_pair_prepare();
 
 // BN (output-channel tile) chosen for a given Cout.
 inline int conv_tile_n(int cout) { return cout >= 128 ? 128 : 64; }
+inline int conv_tile_n(const ConvParams& p) { return p.tile_n == 64 ? 64 : conv_tile_n(p.Cout); }
 
 }  // namespace lm

@@ -4,6 +4,9 @@
 // with log-softmax + argmax, and the TMA stores.  One copy, so that both kernels produce the same bits by construction.
 // The including file defines LM_PROF_T0 / LM_PROF_ADD / LM_EXP (instrumentation of tools/conv_probe) first.
 #pragma once
+#ifndef LM_TMA_STORES
+#define LM_TMA_STORES 0   // 1: the round-1 epilogue (staged rows leave through cp.async.bulk.tensor stores); 0: coalesced 16-byte stores
+#endif
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
 
@@ -18,7 +21,9 @@ constexpr int A_PLANE_BYTES_1x1 = BM * ROW_BYTES;               // 16 KB per pla
 constexpr int F32_ROW_CH = 32;                                  // channels per staged 128-byte row of an fp32 output
 constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB (both planes), 1024-aligned
 constexpr int NUM_A_BUFS = 2;
-constexpr int OUT_STAGE_BYTES = BM * 128;  // output staging: 8 epilogue warps x 4 KB (32 pixels x 32 channels fp32), x2 halves
+// output staging per epilogue warp: with TMA stores a whole 32-pixel plane (4 KB); with direct stores 8 rows at a time
+// (1 KB) - the space saved buys a fourth weight stage for BN = 128
+constexpr int STG_WARP_BYTES = LM_TMA_STORES ? 4096 : 1024;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_THREADS = 256;
@@ -28,7 +33,7 @@ template <int BN>
 struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * B_PLANE_BYTES;      // one weight tile (hi + lo planes) per k-block
-  static constexpr int STAGES = (BN == 64) ? 6 : 3;
+  static constexpr int STAGES = LM_TMA_STORES ? ((BN == 64) ? 6 : 3) : ((BN == 64) ? 7 : 4);
   static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
   static constexpr int NBUF = 512 / ACC_COLS;      // accumulator ring: 2 slots (BN=128), 4 slots (BN=64)
   static constexpr int TMEM_COLS = NBUF * ACC_COLS;
@@ -38,7 +43,16 @@ struct Cfg {
   // other already drains the next tile's chunks and the tensor pipe never waits for a free accumulator slot.
   static constexpr int HALVES = (BN == 64) ? 1 : 2;
   static constexpr int EGROUPS = (BN == 64) ? 2 : 1;
-  static constexpr int DYN_SMEM = NUM_A_BUFS * A_BUF_BYTES + STAGES * STAGE_BYTES + 2 * OUT_STAGE_BYTES + 1024;
+  // Everything lives in dynamic shared memory (declared __align__(1024): the swizzled tiles need it, and no static shared
+  // memory means no alignment slack): activation patches | weight ring | output staging | mbarriers | TMEM base | head
+  static constexpr int NUM_BARS = 2 * STAGES + (EGROUPS + 1) * NBUF + 2 * NUM_A_BUFS;
+  static constexpr int OFF_B = NUM_A_BUFS * A_BUF_BYTES;
+  static constexpr int OFF_STG = OFF_B + STAGES * STAGE_BYTES;
+  static constexpr int OFF_BARS = OFF_STG + (NUM_EPI_THREADS / 32) * STG_WARP_BYTES;
+  static constexpr int OFF_TMEM = OFF_BARS + NUM_BARS * 8;
+  static constexpr int OFF_HEAD = OFF_TMEM + 16;                                   // BN = 64 only: head weights + bias
+  static constexpr int DYN_SMEM = OFF_HEAD + ((BN == 64) ? (MAX_CLASSES * 64 + MAX_CLASSES) * 4 : 0);
+  static_assert(DYN_SMEM <= 232448, "shared-memory budget (227 KB per CTA)");
 };
 
 struct TileCoord {
@@ -137,7 +151,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
     // and the warp's lane 0 hands the buffer to a TMA store - fully coalesced 128 B bursts instead of 32
     // scattered 16-byte stores per warp instruction (16-23k cycles per tile, profiles/r01_conv_role_stalls_v2.log)
     // - with no cross-warp barrier: each epilogue warp streams its own rows out independently.
-    const uint32_t stage = smem_u32(smem_out) + (uint32_t)(warp - EPI_WARP0) * 4096u;
+    const uint32_t stage = smem_u32(smem_out) + (uint32_t)(warp - EPI_WARP0) * (uint32_t)STG_WARP_BYTES;
     const bool issuer = (lane == 0);
     const int ty0 = t.y0 + 4 * q;  // first image row of this warp's 32 pixels
     auto stage_row = [&](uint32_t r, const uint32_t* v8x4) {  // 32 words (128 B) -> row r, chunk j at (j ^ (r & 7))
@@ -175,6 +189,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       }
 #endif
     };
+#if LM_TMA_STORES
     auto round_begin = [&]() {
       if (issuer) tma_store_wait_read();  // this warp's previous store has finished reading the buffer
       __syncwarp();
@@ -183,6 +198,40 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       fence_proxy_async();
       __syncwarp();
     };
+#else
+    // Default since round 2: the staged rows leave with plain 16-byte stores - lanes 8k..8k+7 read the eight pieces of one
+    // 128-byte row (one pixel's channel group: a full line in the channels-last tensor), so every warp instruction writes
+    // four complete lines.  The role-stall profile (profiles/r02_conv_role_stalls.md) showed ~2000 cycles PER ROUND waiting
+    // for the TMA unit to finish reading the staging buffer (it is busy with the operand loads), 8000 - 12000 cycles of
+    // tile-end epilogue during which the tensor pipe ran out of drained accumulator slots on every short-K layer.
+    // The 8 staged rows leave as 16-byte pieces: lanes 8m .. 8m+7 move the eight pieces of staged rows m and m + 4, so every
+    // warp instruction writes four complete 128-byte lines of the channels-last tensor.  `dst` already points at this
+    // lane's piece of row m's pixel; `step` is the distance from row m's pixel to row (m + 4)'s.
+    auto flush8 = [&](uint8_t* dst, size_t step) {
+      const uint32_t m = (uint32_t)lane >> 3, piece = (uint32_t)lane & 7u;
+      uint4 v0, v1;
+      const uint32_t a0 = stage + m * 128u + ((piece ^ m) << 4), a1 = stage + (m + 4u) * 128u + ((piece ^ (m + 4u)) << 4);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w) : "r"(a0) : "memory");
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w) : "r"(a1) : "memory");
+      *reinterpret_cast<uint4*>(dst) = v0;
+      *reinterpret_cast<uint4*>(dst + step) = v1;
+    };
+    // this lane's 128-byte row (its pixel, one channel group of one plane) -> global, image row by image row: the warp's
+    // 32 pixels are 4 image rows of 8; pass k stages the rows of lanes 8k .. 8k+7 (staged row = x) and the warp writes them
+    // out.  `img` = first byte of the (image, plane) in the channels-last tensor, cpix = bytes per pixel, c0 = channel offset.
+    auto emit32 = [&](const uint32_t* v, uint8_t* img, uint32_t cpix, uint32_t c0) {
+      uint8_t* dst = img + ((size_t)ty0 * p.W + t.x0 + (lane >> 3)) * cpix + c0 + (lane & 7) * 16;
+      const size_t pitch = (size_t)p.W * cpix;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __syncwarp();                                     // the previous pass has been read out
+        if ((lane >> 3) == k) stage_row((uint32_t)(lane & 7), v);
+        __syncwarp();
+        flush8(dst, (size_t)4 * cpix);                    // staged rows m and m + 4 are pixels x0 + m and x0 + m + 4
+        dst += pitch;
+      }
+    };
+#endif
 
     if (p.mode == kModeLinear) {
 #pragma unroll
@@ -194,10 +243,15 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
           v[4 * i] = __float_as_uint(acc[g * 32 + 4 * i] + b.x); v[4 * i + 1] = __float_as_uint(acc[g * 32 + 4 * i + 1] + b.y);
           v[4 * i + 2] = __float_as_uint(acc[g * 32 + 4 * i + 2] + b.z); v[4 * i + 3] = __float_as_uint(acc[g * 32 + 4 * i + 3] + b.w);
         }
+#if LM_TMA_STORES
         round_begin();
         stage_row((uint32_t)lane, v);
         round_end();
         if (issuer && !(LM_EXP & 4)) { tma_store_4d(tmOut, stage, cbase + g * F32_ROW_CH, t.x0, ty0, t.n); tma_store_commit(); }
+#else
+        if (!(LM_EXP & 4))
+          emit32(v, static_cast<uint8_t*>(p.out) + (size_t)t.n * p.H * p.W * p.Cout * 4, (uint32_t)p.Cout * 4u, (uint32_t)(cbase + g * F32_ROW_CH) * 4u);
+#endif
       }
     } else {
       const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cbase);
@@ -260,10 +314,16 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
           for (int plane = 0; plane < 2; ++plane) {
             uint32_t v[32];
             pack_row(acc + g * BK, plane, v);
+#if LM_TMA_STORES
             round_begin();
             stage_row((uint32_t)lane, v);
             round_end();
             if (issuer && !(LM_EXP & 4)) { tma_store_5d(tmOut, stage, cbase + g * BK, t.x0, ty0, plane, t.n); tma_store_commit(); }
+#else
+            if (!(LM_EXP & 4))
+              emit32(v, static_cast<uint8_t*>(p.out) + ((size_t)t.n * 2 + plane) * p.H * p.W * p.Cout * kOpBytes, (uint32_t)(p.Cout * kOpBytes),
+                     (uint32_t)((cbase + g * BK) * kOpBytes));
+#endif
           }
         }
         if (p.mode == kModeReluBnPool) {
@@ -284,10 +344,24 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
             for (int plane = 0; plane < 2; ++plane) {
               uint32_t v[32];
               pack_row(pv, plane, v);
+#if LM_TMA_STORES
               round_begin();
               if (writer) stage_row(prow, v);
               round_end();
               if (issuer && !(LM_EXP & 4)) { tma_store_5d(tmPool, stage, cbase + g * BK, t.x0 >> 1, ty0 >> 1, plane, t.n); tma_store_commit(); }
+#else
+              if (!(LM_EXP & 4)) {   // the warp's 8 pooled pixels (2 rows x 4) are one pass
+                __syncwarp();
+                if (writer) stage_row(prow, v);
+                __syncwarp();
+                // staged rows 0..3 = pooled row ty0/2, rows 4..7 = the next pooled row: row m and m + 4 are one image row apart
+                const uint32_t cpix = (uint32_t)(p.Cout * kOpBytes);
+                const int Wp = p.W / 2;
+                uint8_t* img = static_cast<uint8_t*>(p.out_pool) + ((size_t)t.n * 2 + plane) * (p.H / 2) * Wp * cpix;
+                flush8(img + ((size_t)(ty0 >> 1) * Wp + (t.x0 >> 1) + (lane >> 3)) * cpix + (uint32_t)((cbase + g * BK) * kOpBytes) + (lane & 7) * 16,
+                       (size_t)Wp * cpix);
+              }
+#endif
             }
           }
         }
@@ -295,7 +369,9 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
     }
     if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(8);
   }
+#if LM_TMA_STORES
   if (lane == 0) tma_store_wait_all();  // every epilogue warp's issuer: global writes complete before exit
+#endif
 }
 
 }  // namespace

@@ -198,6 +198,7 @@ struct lm_engine {
   uint64_t graph_epoch = 1;
   int use_graphs = 1;     // 0: launch every kernel individually (also whenever per-launch conv timing or score taps are on)
   int64_t graph_launches = 0, graph_hits = 0;
+  unsigned bn64_mask = 0; // bit i: layer i of LAYERS uses BN = 64 output-channel tiles although Cout >= 128 (read at lm_load_weights)
   int dual_issue = 0;     // 1: two MMA-issuing threads per CTA on alternate chunks (conv_tc.cu)
   int cta_pairs = 0;      // 1: the cta_group::2 kernel (conv_tc_pair.cu): bit-identical on hardware, but slower than one CTA per tile
                           //    so far (r02: 14.3 vs 8.7 ms per 37-slice wave, profiles/r02_*) - opt-in
@@ -620,6 +621,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
   if (const char* c = getenv("LM_GRAPHS")) e->use_graphs = atoi(c) != 0;
+  if (const char* c = getenv("LM_BN64_MASK")) e->bn64_mask = (unsigned)strtoul(c, nullptr, 0);
   if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_UPSAMPLE_V2")) e->upsample_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
@@ -753,6 +755,7 @@ int lm_load_weights(lm_engine* e, int slot, const float* blob, size_t n_floats, 
     p.out = L.dst >= 0 ? e->act[L.dst] : nullptr;
     p.out_pool = L.dst_pool >= 0 ? e->act[L.dst_pool] : nullptr;
     p.head_w = s.head_w; p.head_b = s.head_b; p.K = K;
+    p.tile_n = ((e->bn64_mask >> i) & 1u) ? 64 : 0;
     s.params[i] = p;
     int r = make_conv_maps(&s.maps[i], e->act[L.src0], L.src1 >= 0 ? e->act[L.src1] : nullptr, s.lw[i].w, p, e->B);
     if (r) return fail(r, "make_conv_maps failed for layer %d: %d", i, r);
@@ -1219,6 +1222,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!e || !key) return fail(-1, "lm_set_option: NULL argument");
   e->graph_epoch++;   // captured forwards bake the kernel choices in
   if (!strcmp(key, "graphs")) { e->use_graphs = value != 0; return 0; }
+  if (!strcmp(key, "bn64_mask")) { e->bn64_mask = (unsigned)value; return 0; }   // takes effect at the next lm_load_weights
   if (!strcmp(key, "time_convs")) { e->time_convs = value != 0; e->ev_used = 0; return 0; }
   if (!strcmp(key, "post_debug_stage")) { e->post.debug_stage = value; return 0; }
   if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = e->chunk_kb_wide = value; return 0; }

@@ -106,7 +106,7 @@ static float h_param(uint32_t seed, int c, int kind, bool ints) {
   return kind == 1 ? 1.0f + 0.3f * g : 0.2f * g;
 }
 
-static int g_dual = 0, g_pair = 0;
+static int g_dual = 0, g_pair = 0, g_tile_n = 0;   // g_tile_n: forced output-channel tile of the layer being run (0 = auto)
 static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool check, bool ints, int reps) {
   const int Cin = L.C0 + L.C1;
   const float wscale = 1.0f / sqrtf((float)Cin * L.taps) * 1.7f;
@@ -143,7 +143,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
 
   ConvParams p{};
   p.N = N; p.H = L.H; p.W = L.W; p.C0 = L.C0; p.C1 = L.C1; p.Cout = L.Cout; p.taps = L.taps; p.mode = L.mode;
-  p.chunk_kb = chunk_kb; p.dual_issue = g_dual; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
+  p.chunk_kb = chunk_kb; p.dual_issue = g_dual; p.tile_n = g_tile_n; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
   p.head_w = b.hw; p.head_b = b.hb; p.K = L.K; p.labels = b.labels; p.scores = b.scores; p.range_flag = b.range_flag;
   p.in_unscale = 1.f; p.out_scale = 1.f;
   ConvMaps maps;
@@ -262,7 +262,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
       for (int i = 0; i < 6; ++i) pr[i] *= 2;
       pr[9] *= 2;
     } else conv_prof_read(pr);
-    const int BNt = conv_tile_n(L.Cout);
+    const int BNt = g_tile_n == 64 ? 64 : conv_tile_n(L.Cout);
     const double tiles = (double)N * (L.H / 16) * (L.W / 8) * (L.Cout / BNt) * reps;
     const double kbs = tiles * (Cin / kBK) * L.taps;
     const double ctas = std::min<double>(num_sms, tiles / reps) * reps;
@@ -287,6 +287,7 @@ int main(int argc, char** argv) {
   g_dual = argc > 4 ? atoi(argv[4]) : 0;
   g_pair = argc > 5 ? atoi(argv[5]) : 0;
   const int reps = argc > 6 ? atoi(argv[6]) : 3;   // timed repetitions per network layer (0: one untimed launch per layer, for ncu)
+  const unsigned bn64_mask = argc > 7 ? (unsigned)strtoul(argv[7], nullptr, 0) : 0u;   // network layers (bit i) forced to BN = 64 tiles
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
   printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d cta_pairs %d\n", prop.name, sms, batch, chunk, g_dual, g_pair);
@@ -335,7 +336,14 @@ int main(int argc, char** argv) {
       {"up3.block3+head", 256, 256, 64, 0, 64, 9, kModeHead, 3},
   };
   double total_ms = 0;
-  for (const Layer& L : net) total_ms += run_layer(L, batch, chunk, sms, false, false, reps);
+  int li = 0;
+  for (const Layer& L : net) {
+    g_tile_n = ((bn64_mask >> li) & 1u) ? 64 : 0;
+    if (g_tile_n) printf("(BN = 64 tiles) ");
+    total_ms += run_layer(L, batch, chunk, sms, !timing_only && g_tile_n != 0, false, reps);
+    ++li;
+  }
+  g_tile_n = 0;
   printf("TOTAL tensor-core layers: %.3f ms for %d slices -> %.1f slices/s (conv layers only)\n", total_ms, batch,
          batch / total_ms * 1e3);
   printf("conv_probe done\n");
