@@ -5,7 +5,14 @@
 // The including file defines LM_PROF_T0 / LM_PROF_ADD / LM_EXP (instrumentation of tools/conv_probe) first.
 #pragma once
 #ifndef LM_TMA_STORES
-#define LM_TMA_STORES 0   // 1: the round-1 epilogue (staged rows leave through cp.async.bulk.tensor stores); 0: coalesced 16-byte stores
+// 1 (default): staged rows leave through cp.async.bulk.tensor stores out of a 4 KB buffer per epilogue warp, 3 / 6 weight stages.
+// 0: coalesced 16-byte stores out of 8-row staging passes, which frees room for 4 / 7 weight stages - correct (all
+//    CHECKs and GPU tests) but 3.4 % slower per wave on the B200 (profiles/r02_call3_*: 8.78 vs 8.48 ms): the level-0
+//    layers pay for the extra store instructions, the fourth stage buys nothing measurable.
+#define LM_TMA_STORES 1
+#endif
+#ifndef LM_EPI_PREFETCH
+#define LM_EPI_PREFETCH 1
 #endif
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
@@ -101,6 +108,17 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
     float acc[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+#if LM_EPI_PREFETCH
+    {  // the tile-end epilogue starts with 3 x NC per-channel constants (bias, BN scale, BN shift): pull their lines into L1
+       // now, while the tile's chunks are still being computed (the role-stall profile shows the epilogue warps idle here)
+      const int cb0 = t.n0 + ((HALVES == 2) ? ((warp - EPI_WARP0) >> 2) : 0) * NC;
+      if (lane < 3 * (NC * 4 / 128)) {
+        const int arr = lane / (NC * 4 / 128), line = lane % (NC * 4 / 128);
+        const float* base = arr == 0 ? p.bias : (arr == 1 ? p.scale : p.shift);
+        if (base) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + cb0 + line * 32));
+      }
+    }
+#endif
     for (int c = 0; c < num_chunks; ++c) {
       { LM_PROF_T0(); mbar_wait(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
       phase_bits ^= 1u << buf;

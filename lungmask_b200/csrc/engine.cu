@@ -202,7 +202,8 @@ struct lm_engine {
   int dual_issue = 0;     // 1: two MMA-issuing threads per CTA on alternate chunks (conv_tc.cu)
   int cta_pairs = 0;      // 1: the cta_group::2 kernel (conv_tc_pair.cu): bit-identical on hardware, but slower than one CTA per tile
                           //    so far (r02: 14.3 vs 8.7 ms per 37-slice wave, profiles/r02_*) - opt-in
-  int stem_v2 = 1;        // 1 (default): stem_kernel_v2 - weights in registers, 4-pixel quads (bit-identical to stem_kernel, r02 GPU tests)
+  int stem_v2 = 2;        // stem kernel version: 0 stem_kernel, 1 stem_kernel_v2 - weights in registers, 4-pixel quads
+                          // (bit-identical to stem_kernel, r02 GPU tests), 2 (default) stem_kernel_v3 - shared input tile and weights
   int upsample_v2 = 1;    // 1 (default): upsample2x_cells_kernel - one load per output sample (bit-identical to upsample2x_kernel)
   int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
   int chunk_kb_wide = 2;  // ... for the layers with Cout >= 128 (ring of 2 slots: chunk 1 leaves the tensor pipe waiting
@@ -256,8 +257,8 @@ int forward_batch(lm_engine* e, Slot& s, const void* d_in, bool in_f32, int n, u
     RC(launch_stem_f32(static_cast<const float*>(d_in), e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
                        range + A0, s.act_scale[A0], e->stem_v2, e->num_sms, e->st));
   else
-    RC((e->stem_v2 ? launch_stem_v2 : launch_stem)(static_cast<const int16_t*>(d_in), e->act[A0], s.stem_w, s.stem_bias, s.stem_scale,
-                                                   s.stem_shift, n, R, R, range + A0, s.act_scale[A0], e->num_sms, e->st));
+    RC(launch_stem_any(static_cast<const int16_t*>(d_in), e->act[A0], s.stem_w, s.stem_bias, s.stem_scale, s.stem_shift, n, R, R,
+                       range + A0, s.act_scale[A0], e->stem_v2, e->num_sms, e->st));
   e->launches++;
   int up = 0;
   for (int i = 0; i < NUM_LAYERS; ++i) {
@@ -622,7 +623,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
   if (const char* c = getenv("LM_GRAPHS")) e->use_graphs = atoi(c) != 0;
   if (const char* c = getenv("LM_BN64_MASK")) e->bn64_mask = (unsigned)strtoul(c, nullptr, 0);
-  if (const char* c = getenv("LM_STEM_V2")) e->stem_v2 = atoi(c) != 0;
+  if (const char* c = getenv("LM_STEM_V2")) { const int v = atoi(c); e->stem_v2 = v < 0 ? 0 : (v > 2 ? 2 : v); }
   if (const char* c = getenv("LM_UPSAMPLE_V2")) e->upsample_v2 = atoi(c) != 0;
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
   if (const char* c = getenv("LM_MERGE_CTAS")) e->post.merge_ctas = atoi(c) > 0 ? atoi(c) : 0;
@@ -1228,7 +1229,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = e->chunk_kb_wide = value; return 0; }
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
-  if (!strcmp(key, "stem_v2")) { e->stem_v2 = value != 0; return 0; }
+  if (!strcmp(key, "stem_v2")) { if (value < 0 || value > 2) return fail(-1, "stem_v2 must be 0, 1 or 2"); e->stem_v2 = value; return 0; }
   if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value != 0; return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
   if (!strcmp(key, "shard_slab_ccl")) { e->shard_slab_ccl = value != 0; return 0; }

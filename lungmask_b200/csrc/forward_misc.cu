@@ -46,7 +46,10 @@ __device__ __forceinline__ float stem_input(const int16_t* img, size_t idx, cons
   int hu = img[idx];
   hu = hu > 600 ? 600 : hu;  // mask.py:167 (no-op after the clip in utils.py:45)
   const int i = hu + 1024;
-  return i >= 0 ? lut[i] : (float)((double)i / 1624.0);  // mask.py:168 (values below -1024 never come out of preprocess)
+  // mask.py:168.  Values below -1024 never come out of preprocess; for them (and for every other int16 value) the IEEE fp32
+  // quotient of the two exactly representable integers equals the float64 quotient rounded to fp32
+  // (tests/test_host_logic.py::test_normalisation_in_fp32_is_exact) - no double-precision division in the hot loop.
+  return i >= 0 ? lut[i] : __fdiv_rn((float)i, 1624.f);
 }
 __device__ __forceinline__ float stem_input(const float* img, size_t idx, const float*) { return img[idx]; }
 
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const IT* __restrict__ in, op
   // (hu + 1024) / 1624 for every HU value the pre-processing can produce ([-1024, 600]): float64 division, then
   // the cast to fp32 (mask.py:168,178-182), tabulated once per block instead of nine fp64 divisions per thread
   __shared__ float lut[1625];
-  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = (float)((double)i / 1624.0);
+  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 1624.f);
   for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
   if (threadIdx.x < 64) { sb[threadIdx.x] = bias[threadIdx.x]; ss[threadIdx.x] = scale[threadIdx.x]; sh[threadIdx.x] = shift[threadIdx.x]; }
   __syncthreads();
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const IT* __restrict__ in,
                                                       const float* __restrict__ shift,  // [64]
                                                       int N, int H, int W, int* __restrict__ range_flag, float out_scale) {
   __shared__ float lut[1625];
-  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = (float)((double)i / 1624.0);
+  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 1624.f);
   constexpr int TPP = 64 / CPT;  // threads per pixel quad
   const int cq = (int)(threadIdx.x % TPP);
   float wr[CPT][9], br[CPT], sr[CPT], hr[CPT];
@@ -162,6 +165,97 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const IT* __restrict__ in,
       const size_t r = (size_t)y * W + x0 + px;
       op_t* o = out + ((size_t)n * 2 * plane + r) * 64 + cq * CPT;
       split_store(yv, o, o + plane * 64, ovf);
+    }
+  }
+  if (ovf && range_flag) *range_flag = 1;
+}
+
+// stem_kernel_v3 (default since round 2).  ncu / SASS of v1 and v2: instruction-bound - every thread normalised its own
+// 3 x 6 input window (the 8 channel-group threads of a pixel quad eight times the same one, with a double-precision
+// division in the fallback path: 4700 SASS instructions per quad) and reached 1.0 - 1.4 TB/s of the 6.5 TB/s it writes at.
+// Here a block owns an 8-row x 32-column tile of one image: the (8+2) x (32+2) normalised samples are built ONCE in shared
+// memory (zero padding included), the 64 x 9 weights sit in shared memory too ([channel group][tap][8 channels], read as
+// LDS.128 broadcasts: 18 per quad of 4 pixels), and a thread computes 8 channels of a 4-pixel quad from 18 window loads.
+// Same arithmetic in the same order as stem_kernel (fmaf over the taps 0..8 from zero, then ReLU, BN, scale).
+constexpr int S3_TH = 8, S3_TW = 32, S3_PITCH = S3_TW + 2 + 2;   // tile rows / columns, padded row pitch of the input tile
+template <typename IT>
+__global__ void __launch_bounds__(256) stem_kernel_v3(const IT* __restrict__ in, op_t* __restrict__ out,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      int N, int H, int W, int* __restrict__ range_flag, float out_scale) {
+  static_assert(CPT == 8, "stem_kernel_v3 is written for 8 channels per thread (fp16 operand planes)");
+  __shared__ float lut[1625];
+  __shared__ __align__(16) float sw[8][9][8];                 // [channel group][tap][channel within the group]
+  __shared__ __align__(16) float sc[8][3][8];                 // bias / scale / shift per channel group
+  __shared__ float tile[S3_TH + 2][S3_PITCH];
+  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 1624.f);
+  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) { const int c = i / 9, tap = i % 9; sw[c >> 3][tap][c & 7] = w[i]; }
+  if (threadIdx.x < 64) {
+    const int c = threadIdx.x;
+    sc[c >> 3][0][c & 7] = bias[c]; sc[c >> 3][1][c & 7] = scale[c]; sc[c >> 3][2][c & 7] = shift[c];
+  }
+  const int tiles_x = W / S3_TW, tiles_y = H / S3_TH;
+  const int tiles_img = tiles_x * tiles_y;
+  const size_t plane = (size_t)H * W;
+  const int cq = threadIdx.x & 7;            // channel group
+  const int slot = threadIdx.x >> 3;         // 32 quad slots; the tile has 8 rows x 8 quads = 64 quads: two per slot
+  bool ovf = false;
+  for (int tile_id = blockIdx.x; tile_id < N * tiles_img; tile_id += gridDim.x) {
+    const int n = tile_id / tiles_img, r = tile_id - n * tiles_img;
+    const int y0 = (r / tiles_x) * S3_TH, x0 = (r % tiles_x) * S3_TW;
+    const IT* img = in + (size_t)n * plane;
+    __syncthreads();                         // the previous tile has been consumed (and, first time, the tables are ready)
+    for (int i = threadIdx.x; i < (S3_TH + 2) * (S3_TW + 2); i += blockDim.x) {
+      const int ty = i / (S3_TW + 2), tx = i - ty * (S3_TW + 2);
+      const int yy = y0 + ty - 1, xx = x0 + tx - 1;
+      float val = 0.f;                       // zero padding of the convolution
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = stem_input(img, (size_t)yy * W + xx, lut);
+      tile[ty][tx] = val;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int q = slot + 32 * half;        // quad index in the tile: row q / 8, columns 4 * (q % 8) ..
+      const int ty = q >> 3, tx = (q & 7) * 4;
+      float win[3][6];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 6; ++dx) win[dy][dx] = tile[ty + dy][tx + dx];
+      float acc[4][8];
+#pragma unroll
+      for (int px = 0; px < 4; ++px)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[px][e] = 0.f;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[cq][tap][0]), w1 = *reinterpret_cast<const float4*>(&sw[cq][tap][4]);
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+          const float v = win[tap / 3][px + tap % 3];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[px][e] = fmaf(wv[e], v, acc[px][e]);
+        }
+      }
+      float bv[8], sv[8], hv[8];
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(&sc[cq][0][0]), b1 = *reinterpret_cast<const float4*>(&sc[cq][0][4]);
+        const float4 s0 = *reinterpret_cast<const float4*>(&sc[cq][1][0]), s1 = *reinterpret_cast<const float4*>(&sc[cq][1][4]);
+        const float4 h0 = *reinterpret_cast<const float4*>(&sc[cq][2][0]), h1 = *reinterpret_cast<const float4*>(&sc[cq][2][4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        sv[0] = s0.x; sv[1] = s0.y; sv[2] = s0.z; sv[3] = s0.w; sv[4] = s1.x; sv[5] = s1.y; sv[6] = s1.z; sv[7] = s1.w;
+        hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w; hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
+      }
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        float yv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(acc[px][e] + bv[e], 0.f), sv[e]), hv[e]), out_scale);
+        const size_t rpix = (size_t)(y0 + ty) * W + x0 + tx + px;
+        op_t* o = out + ((size_t)n * 2 * plane + rpix) * 64 + cq * 8;
+        split_store(yv, o, o + plane * 64, ovf);
+      }
     }
   }
   if (ovf && range_flag) *range_flag = 1;
@@ -313,7 +407,12 @@ template <typename IT>
 static int launch_stem_t(const IT* in, void* out, const float* w, const float* bias, const float* scale, const float* shift, int N,
                          int H, int W, int* range_flag, float out_scale, int v2, int num_sms, cudaStream_t stream) {
   constexpr int QW = 4;
-  if (v2 && W % QW == 0) {
+  if (v2 >= 2 && W % S3_TW == 0 && H % S3_TH == 0 && CPT == 8) {
+    const int tiles = N * (W / S3_TW) * (H / S3_TH);
+    const int cap = num_sms * 6;
+    stem_kernel_v3<IT><<<tiles < cap ? tiles : cap, 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag,
+                                                                 out_scale);
+  } else if (v2 && W % QW == 0) {
     const size_t threads = (size_t)N * H * (W / QW) * (64 / CPT);
     size_t blocks = (threads + 127) / 128;
     const size_t cap = (size_t)num_sms * 8;
@@ -334,6 +433,10 @@ int launch_stem(const int16_t* in, void* out, const float* w, const float* bias,
 int launch_stem_v2(const int16_t* in, void* out, const float* w, const float* bias, const float* scale,
                    const float* shift, int N, int H, int W, int* range_flag, float out_scale, int num_sms, cudaStream_t stream) {
   return launch_stem_t<int16_t>(in, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, 1, num_sms, stream);
+}
+int launch_stem_any(const int16_t* in, void* out, const float* w, const float* bias, const float* scale, const float* shift, int N, int H,
+                    int W, int* range_flag, float out_scale, int version, int num_sms, cudaStream_t stream) {
+  return launch_stem_t<int16_t>(in, out, w, bias, scale, shift, N, H, W, range_flag, out_scale, version, num_sms, stream);
 }
 int launch_stem_f32(const float* in_norm, void* out, const float* w, const float* bias, const float* scale, const float* shift, int N,
                     int H, int W, int* range_flag, float out_scale, int v2, int num_sms, cudaStream_t stream) {

@@ -65,6 +65,14 @@ def test_volume_dtype_rules():
         _to_engine_volume(np.zeros((4, 4), np.int16))
 
 
+def test_normalisation_in_fp32_is_exact():
+    """mask.py:168 divides in float64 and casts to fp32 (mask.py:178-182); the stem kernels divide the two exactly
+    representable integers in fp32 (IEEE, round to nearest): the same bits for EVERY int16 input, not only [-1024, 600]."""
+    hu = np.minimum(np.arange(-32768, 32768, dtype=np.int64), 600)
+    i = hu + 1024
+    assert np.array_equal((i.astype(np.float64) / 1624.0).astype(np.float32), i.astype(np.float32) / np.float32(1624.0))
+
+
 def test_native_binding_refuses_lossy_conversions():
     from lungmask_b200._native import _as
     assert _as(np.array([[1, 2]], dtype=np.int64), np.int32).dtype == np.int32        # fits: converted
