@@ -1,14 +1,13 @@
 """`lungmask INPUT OUTPUT` command line (flags as lungmask/__main__.py:26-76).
 
-File I/O needs SimpleITK exactly as in the reference (it is outside the accelerated path); `.npy`
-volumes are accepted in addition so the CLI is usable on machines without it.
+Inputs are read by lungmask_b200/io.py (DICOM series directory, NIfTI, MetaImage, .npy - no SimpleITK needed); the
+mask is written with the input's geometry as .nii / .nii.gz / .mha / .npy.
 """
 import argparse
 import os
 import sys
 
-import numpy as np
-
+from .io import load_input_image, save_mask
 from .logger import logger
 from .mask import LMInferer
 
@@ -41,22 +40,7 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     batchsize = 1 if args.cpu else args.batchsize  # __main__.py:81-83
     logger.info("Load model")
-    is_npy = os.path.isfile(args.input) and args.input.endswith(".npy")
-    if is_npy:
-        image, sitk_image = np.load(args.input), None
-    else:
-        try:
-            import SimpleITK as sitk
-        except ImportError:
-            sys.exit("SimpleITK is required to read this input (only .npy volumes work without it)")
-        if os.path.isfile(args.input):
-            sitk_image = sitk.ReadImage(args.input)
-        else:
-            names = sitk.ImageSeriesReader.GetGDCMSeriesFileNames(args.input)
-            if not names:
-                sys.exit("No dicoms found!")
-            sitk_image = sitk.ReadImage(names)
-        image = sitk_image
+    image = load_input_image(args.input, disable_tqdm=args.noprogress, read_metadata=not args.removemetadata)
     if args.modelname == "LTRCLobes_R231":  # __main__.py:95-107
         assert args.modelpath is None, "Modelpath can not be specified for LTRCLobes_R231 fusion"
         inferer = LMInferer(modelname="LTRCLobes", force_cpu=args.cpu, fillmodel="R231", batch_size=batchsize,
@@ -64,15 +48,11 @@ def main(argv=None):
     else:
         inferer = LMInferer(modelname=args.modelname, modelpath=args.modelpath, force_cpu=args.cpu, batch_size=batchsize,
                             volume_postprocessing=not args.nopostprocess, tqdm_disable=args.noprogress)
-    result = inferer.apply(image)
+    result = inferer.apply(image)      # a Volume: orientation handled as for a SimpleITK image (mask.py:157-164, 189-197)
     logger.info(f"Save result to: {args.output}")
-    if sitk_image is None or args.output.endswith(".npy"):
-        np.save(args.output, result)
-    else:
-        import SimpleITK as sitk
-        out = sitk.GetImageFromArray(result)
-        out.CopyInformation(sitk_image)
-        sitk.WriteImage(out, args.output)
+    if not args.removemetadata and image.meta.get("SeriesInstanceUID"):
+        logger.info("DICOM tags are never copied into the output by this build (as with --removemetadata)")
+    save_mask(args.output, result, image)
 
 
 if __name__ == "__main__":

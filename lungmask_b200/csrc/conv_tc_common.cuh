@@ -9,6 +9,7 @@
 // 0: coalesced 16-byte stores out of 8-row staging passes, which frees room for 4 / 7 weight stages - correct (all
 //    CHECKs and GPU tests) but 3.4 % slower per wave on the B200 (profiles/r02_call3_*: 8.78 vs 8.48 ms): the level-0
 //    layers pay for the extra store instructions, the fourth stage buys nothing measurable.
+// 2: coalesced 16-byte stores in ONE sweep out of the 4 KB buffer (3 / 6 weight stages, the TMA configuration's budget).
 #define LM_TMA_STORES 1
 #endif
 #ifndef LM_EPI_PREFETCH
@@ -30,7 +31,7 @@ constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB 
 constexpr int NUM_A_BUFS = 2;
 // output staging per epilogue warp: with TMA stores a whole 32-pixel plane (4 KB); with direct stores 8 rows at a time
 // (1 KB) - the space saved buys a fourth weight stage for BN = 128
-constexpr int STG_WARP_BYTES = LM_TMA_STORES ? 4096 : 1024;
+constexpr int STG_WARP_BYTES = (LM_TMA_STORES == 0) ? 1024 : 4096;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_THREADS = 256;
@@ -40,7 +41,7 @@ template <int BN>
 struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * B_PLANE_BYTES;      // one weight tile (hi + lo planes) per k-block
-  static constexpr int STAGES = LM_TMA_STORES ? ((BN == 64) ? 6 : 3) : ((BN == 64) ? 7 : 4);
+  static constexpr int STAGES = (LM_TMA_STORES != 0) ? ((BN == 64) ? 6 : 3) : ((BN == 64) ? 7 : 4);
   static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
   static constexpr int NBUF = 512 / ACC_COLS;      // accumulator ring: 2 slots (BN=128), 4 slots (BN=64)
   static constexpr int TMEM_COLS = NBUF * ACC_COLS;
@@ -207,7 +208,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       }
 #endif
     };
-#if LM_TMA_STORES
+#if LM_TMA_STORES == 1
     auto round_begin = [&]() {
       if (issuer) tma_store_wait_read();  // this warp's previous store has finished reading the buffer
       __syncwarp();
@@ -240,6 +241,27 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
     auto emit32 = [&](const uint32_t* v, uint8_t* img, uint32_t cpix, uint32_t c0) {
       uint8_t* dst = img + ((size_t)ty0 * p.W + t.x0 + (lane >> 3)) * cpix + c0 + (lane & 7) * 16;
       const size_t pitch = (size_t)p.W * cpix;
+#if LM_TMA_STORES == 2
+      // the whole 32-pixel plane is staged at once (4 KB per warp, as for the TMA stores) and leaves in one sweep
+      __syncwarp();
+      stage_row((uint32_t)lane, v);
+      __syncwarp();
+      {
+        const uint32_t m = (uint32_t)lane >> 3, piece = (uint32_t)lane & 7u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                      // image row k of the warp's four: staged rows 8k + m and 8k + 4 + m
+          uint4 v0, v1;
+          const uint32_t r0 = 8u * k + m, r1 = r0 + 4u;
+          const uint32_t a0 = stage + r0 * 128u + ((piece ^ (r0 & 7u)) << 4), a1 = stage + r1 * 128u + ((piece ^ (r1 & 7u)) << 4);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w) : "r"(a0) : "memory");
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w) : "r"(a1) : "memory");
+          *reinterpret_cast<uint4*>(dst) = v0;
+          *reinterpret_cast<uint4*>(dst + (size_t)4 * cpix) = v1;
+          dst += pitch;
+        }
+      }
+      return;
+#endif
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         __syncwarp();                                     // the previous pass has been read out
@@ -261,7 +283,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
           v[4 * i] = __float_as_uint(acc[g * 32 + 4 * i] + b.x); v[4 * i + 1] = __float_as_uint(acc[g * 32 + 4 * i + 1] + b.y);
           v[4 * i + 2] = __float_as_uint(acc[g * 32 + 4 * i + 2] + b.z); v[4 * i + 3] = __float_as_uint(acc[g * 32 + 4 * i + 3] + b.w);
         }
-#if LM_TMA_STORES
+#if LM_TMA_STORES == 1
         round_begin();
         stage_row((uint32_t)lane, v);
         round_end();
@@ -332,7 +354,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
           for (int plane = 0; plane < 2; ++plane) {
             uint32_t v[32];
             pack_row(acc + g * BK, plane, v);
-#if LM_TMA_STORES
+#if LM_TMA_STORES == 1
             round_begin();
             stage_row((uint32_t)lane, v);
             round_end();
@@ -362,7 +384,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
             for (int plane = 0; plane < 2; ++plane) {
               uint32_t v[32];
               pack_row(pv, plane, v);
-#if LM_TMA_STORES
+#if LM_TMA_STORES == 1
               round_begin();
               if (writer) stage_row(prow, v);
               round_end();
@@ -387,7 +409,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
     }
     if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(8);
   }
-#if LM_TMA_STORES
+#if LM_TMA_STORES == 1
   if (lane == 0) tma_store_wait_all();  // every epilogue warp's issuer: global writes complete before exit
 #endif
 }

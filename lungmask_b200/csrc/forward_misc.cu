@@ -325,15 +325,18 @@ __global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __re
   const int cw = w + 1, ch = h + 1;
   const int H = 2 * h, W = 2 * w;
   const size_t oplane = (size_t)H * W;
-  const size_t total = (size_t)N * ch * cw * cq_per_pix;
+  // (32-bit index arithmetic: N <= 1024 slices x 257 x 257 cells x C / 8 channel groups stays far below 2^32, and the
+  //  64-bit divisions were a third of this kernel's instructions)
+  const uint32_t total = (uint32_t)N * (uint32_t)ch * (uint32_t)cw * (uint32_t)cq_per_pix;
   bool ovf = false;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int cq = (int)(t % cq_per_pix);
-    size_t cell = t / cq_per_pix;
-    const int cj = (int)(cell % cw) - 1;
-    cell /= cw;
-    const int ci = (int)(cell % ch) - 1;
-    const int n = (int)(cell / ch);
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    uint32_t cell = t / (uint32_t)cq_per_pix;
+    const int cq = (int)(t - cell * (uint32_t)cq_per_pix);
+    uint32_t q2 = cell / (uint32_t)cw;
+    const int cj = (int)(cell - q2 * (uint32_t)cw) - 1;
+    const uint32_t q3 = q2 / (uint32_t)ch;
+    const int ci = (int)(q2 - q3 * (uint32_t)ch) - 1;
+    const int n = (int)q3;
     const int ya = ci < 0 ? 0 : ci, yb = ya + 1 < h ? ya + 1 : h - 1;   // the two input rows / columns every sample of the
     const int xa = cj < 0 ? 0 : cj, xb = xa + 1 < w ? xa + 1 : w - 1;   // cell interpolates between (frame cells: clamped)
     const float* base = in + (size_t)n * h * w * C + cq * CPT;

@@ -76,14 +76,25 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
 __device__ __forceinline__ size_t box_volume(const Box& b) {
   return (size_t)(b.z1 - b.z0) * (b.y1 - b.y0) * (b.x1 - b.x0);
 }
-// t-th voxel of the box -> (z,y,x) and linear index in the full volume
+// t-th voxel of the box -> (z,y,x) and linear index in the full volume.  Volumes hold fewer than 2^32 voxels
+// (postprocess_device refuses more), so the index arithmetic is 32-bit: two unsigned divisions instead of four 64-bit
+// ones - the r02 launch list showed the labelling kernels instruction-bound on exactly that.
 __device__ __forceinline__ uint32_t box_voxel(const Box& b, const Dim& d, size_t t, int& z, int& y, int& x) {
-  const int bw = b.x1 - b.x0, bh = b.y1 - b.y0;
-  x = b.x0 + (int)(t % bw);
-  const size_t r = t / bw;
-  y = b.y0 + (int)(r % bh);
-  z = b.z0 + (int)(r / bh);
-  return (uint32_t)(((size_t)z * d.H + y) * d.W + x);
+  const uint32_t bw = (uint32_t)(b.x1 - b.x0), bh = (uint32_t)(b.y1 - b.y0), tt = (uint32_t)t;
+  const uint32_t r = tt / bw;
+  x = b.x0 + (int)(tt - r * bw);
+  const uint32_t zz = r / bh;
+  y = b.y0 + (int)(r - zz * bh);
+  z = b.z0 + (int)zz;
+  return ((uint32_t)z * (uint32_t)d.H + (uint32_t)y) * (uint32_t)d.W + (uint32_t)x;
+}
+// linear index -> (z,y,x), 32-bit
+__device__ __forceinline__ void voxel_zyx(const Dim& d, uint32_t i, int& z, int& y, int& x) {
+  const uint32_t r = i / (uint32_t)d.W;
+  x = (int)(i - r * (uint32_t)d.W);
+  const uint32_t zz = r / (uint32_t)d.H;
+  y = (int)(r - zz * (uint32_t)d.H);
+  z = (int)zz;
 }
 
 // Union-find initialisation.  Consecutive threads hold consecutive voxels of a row, so the x-runs of equal label are
@@ -181,9 +192,9 @@ __global__ void ccl_join_slabs_kernel(const uint8_t* __restrict__ vals, uint32_t
   const size_t HW = (size_t)d.H * d.W;
   const size_t total = (size_t)sb.n * HW;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const int z = sb.z[t / HW];
-    const size_t r = t % HW;
-    const int y = (int)(r / d.W), x = (int)(r % d.W);
+    const uint32_t bi = (uint32_t)t / (uint32_t)HW, r = (uint32_t)t - bi * (uint32_t)HW;
+    const int z = sb.z[bi];
+    const int y = (int)(r / (uint32_t)d.W), x = (int)(r - (uint32_t)y * (uint32_t)d.W);
     const uint32_t i = (uint32_t)((size_t)z * HW + r);
     const uint8_t v = vals[i];
     if (!v || z == 0) continue;
@@ -371,7 +382,8 @@ __global__ void region_stats_kernel(const uint8_t* __restrict__ vals, const uint
     // warp-aggregated area count
     const unsigned peers = __match_any_sync(__activemask(), id);
     if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&area[id], (uint32_t)__popc(peers));
-    const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((size_t)d.W * d.H));
+    int x, y, z;
+    voxel_zyx(d, (uint32_t)i, z, y, x);
     int* bb = bbox + 6 * (size_t)id;
     if (z < bb[0]) atomicMin(&bb[0], z);
     if (z + 1 > bb[1]) atomicMax(&bb[1], z + 1);
@@ -905,7 +917,8 @@ __global__ void keep_complement_kernel(const uint8_t* __restrict__ mapped, const
     const bool keep = mapped[i] == label && parent[i] == root;
     tmp[i] = keep ? 0 : 1;
     if (keep) {
-      const int x = (int)(i % d.W), y = (int)((i / d.W) % d.H), z = (int)(i / ((size_t)d.W * d.H));
+      int x, y, z;
+    voxel_zyx(d, (uint32_t)i, z, y, x);
       if (z < bbox[0]) atomicMin(&bbox[0], z);
       if (z + 1 > bbox[1]) atomicMax(&bbox[1], z + 1);
       if (y < bbox[2]) atomicMin(&bbox[2], y);
@@ -983,11 +996,13 @@ __device__ __forceinline__ int nn_index_f64(int n_in, int n_out, int o) {
   int i = (int)floor(__dadd_rn(c, 0.5));
   return i < 0 ? 0 : (i > n_in - 1 ? n_in - 1 : i);
 }
+template <typename IT>   // uint32_t for volumes below 2^32 voxels (two 32-bit divisions per voxel), size_t otherwise
 __global__ void reshape_kernel(const uint8_t* __restrict__ masks, const int32_t* __restrict__ boxes, int S, int H,
                                int W, int MH, int MW, uint8_t* __restrict__ out) {
   const size_t n = (size_t)S * H * W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W), y = (int)((i / W) % H), s = (int)(i / ((size_t)W * H));
+    const IT ii = (IT)i, row = ii / (IT)W, sl = row / (IT)H;
+    const int x = (int)(ii - row * (IT)W), y = (int)(row - sl * (IT)H), s = (int)sl;
     const int32_t* b = boxes + 4 * s;
     uint8_t v = 0;
     if (y >= b[0] && y < b[2] && x >= b[1] && x < b[3]) {
@@ -1333,7 +1348,8 @@ int keep_largest_component_device(PostScratch& ws, const uint8_t* d_mask, int S,
 int reshape_device(const uint8_t* d_masks, const int32_t* d_boxes, int S, int H, int W, int MH, int MW, uint8_t* d_out,
                    int num_sms, cudaStream_t st) {
   const size_t n = (size_t)S * H * W;
-  reshape_kernel<<<grid_for(n, 256, num_sms), 256, 0, st>>>(d_masks, d_boxes, S, H, W, MH, MW, d_out);
+  if (n < 0xFFFFFFF0ull) reshape_kernel<uint32_t><<<grid_for(n, 256, num_sms), 256, 0, st>>>(d_masks, d_boxes, S, H, W, MH, MW, d_out);
+  else reshape_kernel<size_t><<<grid_for(n, 256, num_sms), 256, 0, st>>>(d_masks, d_boxes, S, H, W, MH, MW, d_out);
   return (int)cudaGetLastError();
 }
 

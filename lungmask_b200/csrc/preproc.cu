@@ -43,7 +43,8 @@ __device__ __forceinline__ int nn_index(const AxisMap& a, int o) {
 struct Smem {
   uint32_t bits[2][T][WORDS];
   uint32_t parent[T * T];
-  uint32_t area[T * T];
+  uint32_t area2[T * T / 2];            // component areas as packed 16-bit counters (an area is at most 128 * 128 = 2^14):
+                                        // 103 KB instead of 135 KB per CTA, so two slices share an SM
   int first_o[2][T], last_o[2][T];      // [axis][thumb index] -> first / last valid output index mapping to it
   int16_t prevp[2][T], nextp[2][T];     // previous / next PRESENT thumb index along each axis
   uint32_t best_key;
@@ -93,7 +94,7 @@ __device__ __forceinline__ bool bit_at(const uint32_t (*b)[WORDS], int r, int c)
 }
 
 template <typename VT>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)   // 64 registers: two CTAs (slices) per SM hide each other's barrier latencies
 bodymask_kernel(const VT* __restrict__ vol, int S, int H, int W, int32_t* __restrict__ boxes,
                 uint8_t* __restrict__ mask_out) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,7 +151,7 @@ bodymask_kernel(const VT* __restrict__ vol, int S, int H, int W, int32_t* __rest
     // (5) largest 4-connected component, first maximum wins (utils.py:75-79)
     for (int i = tid; i < T * T; i += NTHREADS) {
       sm.parent[i] = bit_at(sm.bits[0], i / T, i % T) ? (uint32_t)i : NONE;
-      sm.area[i] = 0;
+      if ((i & 1) == 0) sm.area2[i >> 1] = 0;
     }
     if (tid == 0) { sm.best_key = 0; sm.min_root = NONE; }
     __syncthreads();
@@ -162,10 +163,16 @@ bodymask_kernel(const VT* __restrict__ vol, int S, int H, int W, int32_t* __rest
     }
     __syncthreads();
     for (int i = tid; i < T * T; i += NTHREADS)
-      if (sm.parent[i] != NONE) atomicAdd(&sm.area[uf_find(sm.parent, i)], 1u);
+      if (sm.parent[i] != NONE) {
+        const uint32_t root = uf_find(sm.parent, i);
+        atomicAdd(&sm.area2[root >> 1], (root & 1u) ? 0x10000u : 1u);   // no carry between the halves: areas stay below 2^16
+      }
     __syncthreads();
     for (int i = tid; i < T * T; i += NTHREADS)
-      if (sm.parent[i] == (uint32_t)i) atomicMax(&sm.best_key, (sm.area[i] << 14) | (uint32_t)(T * T - 1 - i));
+      if (sm.parent[i] == (uint32_t)i) {
+        const uint32_t area = (sm.area2[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+        atomicMax(&sm.best_key, (area << 14) | (uint32_t)(T * T - 1 - i));
+      }
     __syncthreads();
     const bool any_region = sm.best_key != 0;
     if (any_region) {
@@ -400,7 +407,7 @@ static int launch_bodymask_t(const VT* vol, int S, int H, int W, int32_t* boxes,
     if (e != cudaSuccess) return (int)e;
     attr_set_mask.fetch_or(1ull << dev, std::memory_order_release);   // (benign race: setting the attribute twice is harmless)
   }
-  const int grid = S < num_sms ? S : num_sms;
+  const int grid = S < 2 * num_sms ? S : 2 * num_sms;
   bodymask_kernel<VT><<<grid, NTHREADS, sizeof(Smem), stream>>>(vol, S, H, W, boxes, mask_out);
   return (int)cudaGetLastError();
 }

@@ -267,13 +267,29 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Remote arrives of the pair kernel.  LM_PAIR_ARRIVE selects their memory semantics:
+//   0  .release.cluster  (round-1 version: a cluster-scope release in front of every arrive - measured at about 1000
+//                         cycles per arrive, profiles/r02_conv_role_stalls.md)
+//   1  default (.release.cta) - what the hand-shakes need: the data they order is TMEM (tcgen05.wait::ld +
+//      tcgen05.fence::before_thread_sync precede the arrive) or written by TMA (complete_tx), never generic stores
+//   2  .relaxed.cluster
+#ifndef LM_PAIR_ARRIVE
+#define LM_PAIR_ARRIVE 1
+#endif
+#if LM_PAIR_ARRIVE == 0
+#define LM_PAIR_SEM ".release.cluster"
+#elif LM_PAIR_ARRIVE == 1
+#define LM_PAIR_SEM ""
+#else
+#define LM_PAIR_SEM ".relaxed.cluster"
+#endif
 // arrive (count 1) on the mbarrier at the same shared-memory offset in the pair's leader CTA (rank 0)
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+  asm volatile("mbarrier.arrive" LM_PAIR_SEM ".shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
 // leader's own arrive + transaction bytes of BOTH CTAs' loads (the peer's TMA completes on the leader's barrier)
 __device__ __forceinline__ void mbar_arrive_expect_tx_leader(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar & kPeerBitMask), "r"(bytes)
+  asm volatile("mbarrier.arrive.expect_tx" LM_PAIR_SEM ".shared::cluster.b64 _, [%0], %1;" ::"r"(bar & kPeerBitMask), "r"(bytes)
                : "memory");
 }
 // TMA loads into this CTA's shared memory whose completion is signalled on the LEADER's mbarrier

@@ -206,13 +206,16 @@ class LMInferer:
         return self._run(array, orient.orientation_from_direction(direction))
 
     def apply(self, image) -> np.ndarray:
-        """Segments a volume: numpy (slices, H, W) or sitk.Image -> uint8 labels of the same shape
+        """Segments a volume: numpy (slices, H, W), sitk.Image or lungmask_b200.io.Volume -> uint8 labels of the same shape
         (lungmask/mask.py:212-232).  The input is not modified."""
         if isinstance(image, np.ndarray):
             return self._run(image)
+        from .io import Volume
+        if isinstance(image, Volume):       # what lungmask_b200.io.load_input_image returns
+            return self.apply_oriented(image.array, image.GetDirection())
         sitk = self._sitk()
         if sitk is None or not isinstance(image, sitk.Image):
-            raise TypeError("apply() expects a numpy array or a SimpleITK image")
+            raise TypeError("apply() expects a numpy array, a SimpleITK image or a lungmask_b200.io.Volume")
         return self.apply_oriented(sitk.GetArrayFromImage(image), image.GetDirection())
 
 

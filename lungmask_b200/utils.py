@@ -3,13 +3,15 @@
 Same names and argument meaning as the reference (`preprocess`, `simple_bodymask`, `crop_and_resize`,
 `reshape_mask`, `postprocessing`, `keep_largest_connected_component`, `bbox_3D`; lungmask/utils.py:32-129,272-404) so that the reference's
 own known-answer tests (tests/test_utils.py:58-107,124-159) run unchanged against them.  Image I/O
-(`read_dicoms`, `load_input_image`) is outside the accelerated path and lives in the CLI module.
+(`read_dicoms`, `load_input_image`; utils.py:132-269) is re-exported from lungmask_b200/io.py, a SimpleITK-free reader
+that returns `Volume` objects (array + geometry) instead of sitk images.
 """
 import os
 
 import numpy as np
 
 from . import _native
+from .io import load_input_image, read_dicoms  # noqa: F401  (reference names, utils.py:132,235)
 
 _engine = None
 

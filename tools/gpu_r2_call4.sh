@@ -3,9 +3,9 @@
 # c: direct stores + prefetch), stem_kernel_v3 (bit-identity + timing + ncu), full GPU suite, bench lines.
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-for v in a b c; do timeout 100 tools/conv_probe_$v 37 2 1 0 0 > $O/r4_probe_$v.log 2>&1; echo "variant $v: $(grep TOTAL $O/r4_probe_$v.log)"; done
+for v in a b c d; do timeout 100 tools/conv_probe_$v 37 2 1 0 0 > $O/r4_probe_$v.log 2>&1; echo "variant $v: $(grep TOTAL $O/r4_probe_$v.log)"; done
 timeout 200 tools/conv_probe 37 2 0 0 0 > $O/r4_probe_default.log 2>&1; grep -E "FAIL|TOTAL" $O/r4_probe_default.log | cut -c1-160
-paste <(grep TIME $O/r4_probe_a.log | awk '{print $2, $(NF-3)}') <(grep TIME $O/r4_probe_b.log | awk '{print $(NF-3)}') <(grep TIME $O/r4_probe_c.log | awk '{print $(NF-3)}')
+paste <(grep TIME $O/r4_probe_a.log | awk '{print $2, $(NF-3)}') <(grep TIME $O/r4_probe_b.log | awk '{print $(NF-3)}') <(grep TIME $O/r4_probe_c.log | awk '{print $(NF-3)}') <(grep TIME $O/r4_probe_d.log | awk '{print $(NF-3)}')
 timeout 120 tools/conv_probe_prof 37 2 1 0 0 > $O/r4_prof_default_c2.log 2>&1; grep PROF $O/r4_prof_default_c2.log | cut -c1-250 | head -8
 timeout 300 python -m pytest tests/test_gpu_zz_experimental.py tests/test_gpu_forward.py -m gpu -q -s > $O/r4_pytest_fast.log 2>&1; echo "fast pytest rc=$?"; tail -3 $O/r4_pytest_fast.log
 timeout 400 python bench.py --steps 5 --warmup 3 > $O/r4_bench_C2.json 2> $O/r4_bench_C2.err; echo "bench C2 rc=$?"
