@@ -25,6 +25,7 @@ oracle on the bounded sample the CPU baseline is timed on.
 import argparse
 import json
 import os
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not precede the JSON line on stdout
 import subprocess
 import sys
 import threading

@@ -146,6 +146,7 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
         const uint32_t s_cur = s;
         // ---- first part of the burst
         if (mine) {
+          LM_PROF_T0();
           tc_fence_after();
           if (first) {
             // first k-step of a chunk: hi*hi restarts from zero; the corrections restart only at the slot's first
@@ -158,6 +159,7 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
           if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + A_PLANE), hi_b | blo, idesc_corr);  // lo*hi
           LM_UMMA_C<true>(d_tmem, hi_a | (alo + 2u), hi_b | (blo + 2u), idesc_wide);
           if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + A_PLANE + 2u), hi_b | (blo + 2u), idesc_corr);
+          LM_PROF_ADD(10);   // issuing the first two k-steps of the k-block (the thread blocks here when the MMA queue is full)
         }
         // ---- close the bookkeeping of this k-block, advance to the next one and wait for its barriers
         --kb_left;
@@ -177,14 +179,20 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
         if (has_next) { LM_PROF_T0(); mbar_wait(g.full0 + 8 * s, ph); LM_PROF_ADD(4); }
         // ---- rest of the burst, then the releases
         if (mine) {
+          LM_PROF_T0();
 #pragma unroll
           for (int k = 2; k < ROW_BYTES / 32; ++k) {
             const uint32_t ko = (uint32_t)(k * 2);  // one MMA k-step = 32 B along K (16 fp16 / 8 tf32), >>4
             LM_UMMA_C<true>(d_tmem, hi_a | (alo + ko), hi_b | (blo + ko), idesc_wide);
             if (!(LM_EXP & 1)) LM_UMMA_C<true>(d_tmem + BN, hi_a | (alo + A_PLANE + ko), hi_b | (blo + ko), idesc_corr);
           }
-          umma_commit(g.empty0 + 8 * s_cur);           // weight stage consumed (only this issuer read it)
-          if (chunk_end) umma_commit(tfull_cur);       // chunk complete -> the tile's epilogue group may drain it
+          LM_PROF_ADD(11);   // the other two k-steps
+          {
+            LM_PROF_T0();
+            umma_commit(g.empty0 + 8 * s_cur);           // weight stage consumed (only this issuer read it)
+            if (chunk_end) umma_commit(tfull_cur);       // chunk complete -> the tile's epilogue group may drain it
+            LM_PROF_ADD(12);
+          }
         }
         if (tap == TAPS - 1) umma_commit(g.aempty0 + 8 * ab_cur);  // arrives once this issuer's MMAs on the buffer have retired
         // the accumulator slot of the next chunk is awaited LAST: with a two-slot ring it is the one hand-shake that
@@ -262,6 +270,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // Both single-issuer roles run as warp-uniform loops (all 32 lanes execute the control flow and poll the
   // barriers, one elected lane issues the TMA / MMA / commit): loop state then lives in uniform registers
   // and the issue thread is not throttled by divergent-code bookkeeping.
+  // Register reallocation (setmaxnreg): warps 0-3 (producer, issuer(s), TMEM allocator) give registers to the two epilogue
+  // warpgroups, whose chunk drains hold 3 x 64 fp32 values per thread: 128 x LM_REGS_LOW + 256 x LM_REGS_HIGH <= 384 x 168.
+  // Each branch starts with its warpgroups' setmaxnreg and the branches only meet again at the kernel's last barrier.
+  if (warp >= EPI_WARP0) {
+#if LM_SETMAXNREG
+    setmaxnreg_inc<LM_REGS_HIGH>();
+#endif
+    // ------------------------------------------------------------------ epilogue warps
+    conv_epilogue_warps<BN, false>(p, &tmOut, &tmPool, tmem_base, tfull0, tempty0, smem_out, reinterpret_cast<float*>(smem + C::OFF_CONST), s_head_w, s_head_b, (int)blockIdx.x,
+                                   total_tiles, (int)gridDim.x, [](int item) { return item; }, num_chunks);
+    tc_fence_before();
+    __syncthreads();   // the kernel's last barrier (the other warps arrive at it from their own branch)
+    return;
+  } else {
+#if LM_SETMAXNREG
+    setmaxnreg_dec<LM_REGS_LOW>();
+#endif
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t s = 0, ph = 0, ab = 0, aph = 0;
@@ -315,10 +340,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------------------------ epilogue warps
-    conv_epilogue_warps<BN, false>(p, &tmOut, &tmPool, tmem_base, tfull0, tempty0, smem_out, s_head_w, s_head_b, (int)blockIdx.x,
-                                   total_tiles, (int)gridDim.x, [](int item) { return item; }, num_chunks);
+  }
   }
   tc_fence_before();
   __syncthreads();

@@ -5,15 +5,19 @@
 // The including file defines LM_PROF_T0 / LM_PROF_ADD / LM_EXP (instrumentation of tools/conv_probe) first.
 #pragma once
 #ifndef LM_TMA_STORES
-// 1 (default): staged rows leave through cp.async.bulk.tensor stores out of a 4 KB buffer per epilogue warp, 3 / 6 weight stages.
-// 0: coalesced 16-byte stores out of 8-row staging passes, which frees room for 4 / 7 weight stages - correct (all
-//    CHECKs and GPU tests) but 3.4 % slower per wave on the B200 (profiles/r02_call3_*: 8.78 vs 8.48 ms): the level-0
-//    layers pay for the extra store instructions, the fourth stage buys nothing measurable.
-// 2: coalesced 16-byte stores in ONE sweep out of the 4 KB buffer (3 / 6 weight stages, the TMA configuration's budget).
+// 1 (default): staged rows leave through cp.async.bulk.tensor stores out of a 4 KB buffer per epilogue warp.
+// 2: coalesced 16-byte stores in ONE sweep out of the same buffer: equal within 0.5 % per wave (5 % faster on the pooled
+//    level-0 layer, 4 % slower on the two other 256 x 256 layers; profiles/r02_call5_summary.md).
+// (Round 2 also measured 8-row staging passes with a fourth weight stage: 3.4 % slower, removed; and an L1 prefetch of the
+//  per-channel constants: no gain, superseded by the shared-memory copy below.)
 #define LM_TMA_STORES 1
 #endif
-#ifndef LM_EPI_PREFETCH
-#define LM_EPI_PREFETCH 1
+#ifndef LM_SETMAXNREG
+#define LM_SETMAXNREG 1
+#endif
+#ifndef LM_REGS_LOW
+#define LM_REGS_LOW 88
+#define LM_REGS_HIGH 208
 #endif
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
@@ -29,9 +33,8 @@ constexpr int A_PLANE_BYTES_1x1 = BM * ROW_BYTES;               // 16 KB per pla
 constexpr int F32_ROW_CH = 32;                                  // channels per staged 128-byte row of an fp32 output
 constexpr int A_BUF_BYTES = 2 * A_PLANE_BYTES_3x3;           // 46080 B = 45 KB (both planes), 1024-aligned
 constexpr int NUM_A_BUFS = 2;
-// output staging per epilogue warp: with TMA stores a whole 32-pixel plane (4 KB); with direct stores 8 rows at a time
-// (1 KB) - the space saved buys a fourth weight stage for BN = 128
-constexpr int STG_WARP_BYTES = (LM_TMA_STORES == 0) ? 1024 : 4096;
+constexpr int STG_WARP_BYTES = 4096;    // output staging per epilogue warp: one 32-pixel plane of 64 channels
+constexpr int CONST_WARP_FLOATS = 3 * 64;  // per epilogue warp: bias | BN scale | BN shift of the 64 channels its threads hold
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_THREADS = 256;
@@ -41,7 +44,7 @@ template <int BN>
 struct Cfg {
   static constexpr int B_PLANE_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * B_PLANE_BYTES;      // one weight tile (hi + lo planes) per k-block
-  static constexpr int STAGES = (LM_TMA_STORES != 0) ? ((BN == 64) ? 6 : 3) : ((BN == 64) ? 7 : 4);
+  static constexpr int STAGES = (BN == 64) ? 6 : 3;
   static constexpr int ACC_COLS = 2 * BN;          // [0,BN) hi*hi, [BN,2BN) hi*lo + lo*hi
   static constexpr int NBUF = 512 / ACC_COLS;      // accumulator ring: 2 slots (BN=128), 4 slots (BN=64)
   static constexpr int TMEM_COLS = NBUF * ACC_COLS;
@@ -52,11 +55,13 @@ struct Cfg {
   static constexpr int HALVES = (BN == 64) ? 1 : 2;
   static constexpr int EGROUPS = (BN == 64) ? 2 : 1;
   // Everything lives in dynamic shared memory (declared __align__(1024): the swizzled tiles need it, and no static shared
-  // memory means no alignment slack): activation patches | weight ring | output staging | mbarriers | TMEM base | head
+  // memory means no alignment slack): activation patches | weight ring | output staging | per-channel constants |
+  // mbarriers | TMEM base | head
   static constexpr int NUM_BARS = 2 * STAGES + (EGROUPS + 1) * NBUF + 2 * NUM_A_BUFS;
   static constexpr int OFF_B = NUM_A_BUFS * A_BUF_BYTES;
   static constexpr int OFF_STG = OFF_B + STAGES * STAGE_BYTES;
-  static constexpr int OFF_BARS = OFF_STG + (NUM_EPI_THREADS / 32) * STG_WARP_BYTES;
+  static constexpr int OFF_CONST = OFF_STG + (NUM_EPI_THREADS / 32) * STG_WARP_BYTES;
+  static constexpr int OFF_BARS = OFF_CONST + (NUM_EPI_THREADS / 32) * CONST_WARP_FLOATS * 4;
   static constexpr int OFF_TMEM = OFF_BARS + NUM_BARS * 8;
   static constexpr int OFF_HEAD = OFF_TMEM + 16;                                   // BN = 64 only: head weights + bias
   static constexpr int DYN_SMEM = OFF_HEAD + ((BN == 64) ? (MAX_CLASSES * 64 + MAX_CLASSES) * 4 : 0);
@@ -85,7 +90,7 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, int n_tiles, int tile
 template <int BN, bool PAIR, typename TileOf>
 __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const CUtensorMap* tmOut, const CUtensorMap* tmPool,
                                                     uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0, uint8_t* smem_out,
-                                                    const float* s_head_w, const float* s_head_b, int first_item,
+                                                    float* smem_const, const float* s_head_w, const float* s_head_b, int first_item,
                                                     int total_items, int item_step, TileOf tile_of, int num_chunks) {
   using C = Cfg<BN>;
   constexpr int NBUF = C::NBUF;
@@ -103,25 +108,39 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
   uint32_t buf = 0;          // ring slot of the next chunk (all tiles, both groups, advance it)
   uint32_t phase_bits = 0;   // bit b: parity this group's next wait on slot b expects (its own barrier set)
   uint32_t tseq = 0;
+  float* cst = smem_const + (warp - EPI_WARP0) * CONST_WARP_FLOATS;   // this warp's bias | scale | shift (NC = 64 each)
+  int const_n0 = -1;                                                  // channel block they belong to
+  static_assert(NC == 64, "one epilogue thread holds 64 accumulator columns");
   for (int item = first_item; item < total_items; item += item_step, ++tseq) {
     if (EGROUPS == 2 && (tseq & 1u) != egroup) { buf = (buf + (uint32_t)num_chunks) % NBUF; continue; }  // the other group's tile
     const TileCoord t = decode_tile(tile_of(item), n_tiles, tiles_x, tiles_img, BN);
     float acc[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) acc[i] = 0.f;
-#if LM_EPI_PREFETCH
-    {  // the tile-end epilogue starts with 3 x NC per-channel constants (bias, BN scale, BN shift): pull their lines into L1
-       // now, while the tile's chunks are still being computed (the role-stall profile shows the epilogue warps idle here)
-      const int cb0 = t.n0 + ((HALVES == 2) ? ((warp - EPI_WARP0) >> 2) : 0) * NC;
-      if (lane < 3 * (NC * 4 / 128)) {
-        const int arr = lane / (NC * 4 / 128), line = lane % (NC * 4 / 128);
-        const float* base = arr == 0 ? p.bias : (arr == 1 ? p.scale : p.shift);
-        if (base) asm volatile("prefetch.global.L1 [%0];" ::"l"(base + cb0 + line * 32));
+    if (t.n0 != const_n0) {
+      // The tile-end epilogue needs 3 x NC per-channel constants.  Read from global memory there they were its largest
+      // stall (long-scoreboard waits on 48 dependent-use LDG.128 per thread with two warps per scheduler to hide them,
+      // ncu source view of round 2); the warp copies them into its own 768 bytes of shared memory now - one coalesced
+      // LDG per lane, in flight while the tile's chunks are computed - and reads them back as broadcast LDS.128.
+      const_n0 = t.n0;
+      const int cb0 = t.n0 + half * NC;
+      __syncwarp();                                        // the previous tile's reads are done
+      {
+        const int arr = lane >> 4, i4 = lane & 15;         // lanes 0-15: bias, 16-31: scale; then lanes 0-15: shift
+        const float* src = arr == 0 ? p.bias : p.scale;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src) v = __ldg(reinterpret_cast<const float4*>(src + cb0) + i4);
+        reinterpret_cast<float4*>(cst)[lane] = v;
+        if (lane < 16) {
+          float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.shift) h = __ldg(reinterpret_cast<const float4*>(p.shift + cb0) + i4);
+          reinterpret_cast<float4*>(cst)[32 + lane] = h;
+        }
       }
+      __syncwarp();
     }
-#endif
     for (int c = 0; c < num_chunks; ++c) {
-      { LM_PROF_T0(); mbar_wait(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
+      { LM_PROF_T0(); mbar_wait<1>(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
       phase_bits ^= 1u << buf;
       tc_fence_after();
       LM_PROF_T0();
@@ -156,14 +175,12 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       if (++buf == NBUF) buf = 0;
     }
     LM_PROF_T0();
-    {  // undo the operands' power-of-two scales (1.0 unless the engine rescaled a tensor: exact either way)
-      const float unscale = p.in_unscale;
-#pragma unroll
-      for (int i = 0; i < NC; ++i) acc[i] = __fmul_rn(acc[i], unscale);
-    }
+    // acc * in_unscale undoes the operands' power-of-two scales (1.0 unless the engine rescaled a tensor).  The product is
+    // exact, so fma(acc, unscale, bias) below rounds exactly like the separate multiply and add.
+    const float unscale = p.in_unscale;
     const int y = t.y0 + hl, x = t.x0 + wl;
     const int cbase = t.n0 + half * NC;
-    const float4* bias4 = reinterpret_cast<const float4*>(p.bias + cbase);
+    const float4* bias4 = reinterpret_cast<const float4*>(cst);             // shared memory, all lanes read the same address
 
     // The tile leaves through shared memory: every thread drops its pixel's 32-channel groups as 128-byte
     // rows (128B-swizzled, conflict-free) into its WARP's 4 KB staging buffer (32 pixels = 4 image rows x 8)
@@ -218,14 +235,9 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       __syncwarp();
     };
 #else
-    // Default since round 2: the staged rows leave with plain 16-byte stores - lanes 8k..8k+7 read the eight pieces of one
-    // 128-byte row (one pixel's channel group: a full line in the channels-last tensor), so every warp instruction writes
-    // four complete lines.  The role-stall profile (profiles/r02_conv_role_stalls.md) showed ~2000 cycles PER ROUND waiting
-    // for the TMA unit to finish reading the staging buffer (it is busy with the operand loads), 8000 - 12000 cycles of
-    // tile-end epilogue during which the tensor pipe ran out of drained accumulator slots on every short-K layer.
-    // The 8 staged rows leave as 16-byte pieces: lanes 8m .. 8m+7 move the eight pieces of staged rows m and m + 4, so every
-    // warp instruction writes four complete 128-byte lines of the channels-last tensor.  `dst` already points at this
-    // lane's piece of row m's pixel; `step` is the distance from row m's pixel to row (m + 4)'s.
+    // LM_TMA_STORES == 2: the staged rows leave with plain 16-byte stores - lanes 8m .. 8m+7 read the eight pieces of one
+    // 128-byte row (one pixel's channel group: a full line of the channels-last tensor), so every warp instruction writes
+    // four complete lines.  flush8: staged rows m and m + 4 -> `dst` and `dst + step` (the warp's 8 pooled pixels are one call).
     auto flush8 = [&](uint8_t* dst, size_t step) {
       const uint32_t m = (uint32_t)lane >> 3, piece = (uint32_t)lane & 7u;
       uint4 v0, v1;
@@ -235,13 +247,12 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       *reinterpret_cast<uint4*>(dst) = v0;
       *reinterpret_cast<uint4*>(dst + step) = v1;
     };
-    // this lane's 128-byte row (its pixel, one channel group of one plane) -> global, image row by image row: the warp's
-    // 32 pixels are 4 image rows of 8; pass k stages the rows of lanes 8k .. 8k+7 (staged row = x) and the warp writes them
-    // out.  `img` = first byte of the (image, plane) in the channels-last tensor, cpix = bytes per pixel, c0 = channel offset.
+    // emit32: this lane's 128-byte row (its pixel, one channel group of one plane) -> global.  The warp's 32 pixels are 4
+    // image rows of 8.  `img` = first byte of the (image, plane) in the channels-last tensor, cpix = bytes per pixel,
+    // c0 = channel offset in bytes.
     auto emit32 = [&](const uint32_t* v, uint8_t* img, uint32_t cpix, uint32_t c0) {
       uint8_t* dst = img + ((size_t)ty0 * p.W + t.x0 + (lane >> 3)) * cpix + c0 + (lane & 7) * 16;
       const size_t pitch = (size_t)p.W * cpix;
-#if LM_TMA_STORES == 2
       // the whole 32-pixel plane is staged at once (4 KB per warp, as for the TMA stores) and leaves in one sweep
       __syncwarp();
       stage_row((uint32_t)lane, v);
@@ -260,16 +271,6 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
           dst += pitch;
         }
       }
-      return;
-#endif
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        __syncwarp();                                     // the previous pass has been read out
-        if ((lane >> 3) == k) stage_row((uint32_t)(lane & 7), v);
-        __syncwarp();
-        flush8(dst, (size_t)4 * cpix);                    // staged rows m and m + 4 are pixels x0 + m and x0 + m + 4
-        dst += pitch;
-      }
     };
 #endif
 
@@ -279,9 +280,9 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
         uint32_t v[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 b = __ldg(bias4 + g * 8 + i);
-          v[4 * i] = __float_as_uint(acc[g * 32 + 4 * i] + b.x); v[4 * i + 1] = __float_as_uint(acc[g * 32 + 4 * i + 1] + b.y);
-          v[4 * i + 2] = __float_as_uint(acc[g * 32 + 4 * i + 2] + b.z); v[4 * i + 3] = __float_as_uint(acc[g * 32 + 4 * i + 3] + b.w);
+          const float4 b = bias4[g * 8 + i];
+          v[4 * i] = __float_as_uint(__fmaf_rn(acc[g * 32 + 4 * i], unscale, b.x)); v[4 * i + 1] = __float_as_uint(__fmaf_rn(acc[g * 32 + 4 * i + 1], unscale, b.y));
+          v[4 * i + 2] = __float_as_uint(__fmaf_rn(acc[g * 32 + 4 * i + 2], unscale, b.z)); v[4 * i + 3] = __float_as_uint(__fmaf_rn(acc[g * 32 + 4 * i + 3], unscale, b.w));
         }
 #if LM_TMA_STORES == 1
         round_begin();
@@ -294,18 +295,18 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
 #endif
       }
     } else {
-      const float4* scale4 = reinterpret_cast<const float4*>(p.scale + cbase);
-      const float4* shift4 = reinterpret_cast<const float4*>(p.shift + cbase);
+      const float4* scale4 = bias4 + NC / 4;
+      const float4* shift4 = bias4 + 2 * (NC / 4);
       // y = relu(acc + bias) * scale + shift   (Conv -> ReLU -> BatchNorm(eval), resunet.py:93-105)
 #pragma unroll
       for (int i = 0; i < NC / 4; ++i) {
-        const float4 b = __ldg(bias4 + i), s = __ldg(scale4 + i), h = __ldg(shift4 + i);
-        acc[4 * i + 0] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 0] + b.x, 0.f), s.x), h.x);
-        acc[4 * i + 1] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 1] + b.y, 0.f), s.y), h.y);
-        acc[4 * i + 2] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 2] + b.z, 0.f), s.z), h.z);
-        acc[4 * i + 3] = __fadd_rn(__fmul_rn(fmaxf(acc[4 * i + 3] + b.w, 0.f), s.w), h.w);
+        const float4 b = bias4[i], s = scale4[i], h = shift4[i];
+        acc[4 * i + 0] = __fadd_rn(__fmul_rn(fmaxf(__fmaf_rn(acc[4 * i + 0], unscale, b.x), 0.f), s.x), h.x);
+        acc[4 * i + 1] = __fadd_rn(__fmul_rn(fmaxf(__fmaf_rn(acc[4 * i + 1], unscale, b.y), 0.f), s.y), h.y);
+        acc[4 * i + 2] = __fadd_rn(__fmul_rn(fmaxf(__fmaf_rn(acc[4 * i + 2], unscale, b.z), 0.f), s.z), h.z);
+        acc[4 * i + 3] = __fadd_rn(__fmul_rn(fmaxf(__fmaf_rn(acc[4 * i + 3], unscale, b.w), 0.f), s.w), h.w);
       }
-      if (p.mode == kModeHead) {
+      if (BN == 64 && p.mode == kModeHead) {   // (the head follows a 64-channel layer: no head code in the BN = 128 kernel)
         // 1x1 head (resunet.py:69): this thread holds all 64 channels of its pixel (BN = 64 rows are not split).
         float lg[MAX_CLASSES];
         float mx = -INFINITY;

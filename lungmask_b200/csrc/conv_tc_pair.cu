@@ -217,6 +217,21 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const long long prof_kernel_t0 = clock64();
 #endif
 
+  // Register reallocation (setmaxnreg): warps 0-3 (producer, issuer(s), TMEM allocator) give registers to the two epilogue
+  // warpgroups, whose chunk drains hold 3 x 64 fp32 values per thread: 128 x LM_REGS_LOW + 256 x LM_REGS_HIGH <= 384 x 168.
+  // Each branch starts with its warpgroups' setmaxnreg and the branches only meet again at the kernel's last barrier.
+  if (warp >= EPI_WARP0) {
+#if LM_SETMAXNREG
+    setmaxnreg_inc<LM_REGS_HIGH>();
+#endif
+    // ------------------------------------------------------------------ epilogue warps
+    // the pair's work items are tile PAIRS; this CTA drains and stores its own tile of each pair (conv_tc_common.cuh)
+    conv_epilogue_warps<BN, true>(p, &tmOut, &tmPool, tmem_base, tfull0, tempty0, smem_out, reinterpret_cast<float*>(smem + C::OFF_CONST), s_head_w, s_head_b, first_pair, total_pairs,
+                                  pair_step, my_tile, num_chunks);
+  } else {
+#if LM_SETMAXNREG
+    setmaxnreg_dec<LM_REGS_LOW>();
+#endif
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     uint32_t s = 0, ph = 0, ab = 0, aph = 0;
@@ -260,11 +275,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if (taps == 9) mma_issue_loop_pair<BN, 9>(ia); else mma_issue_loop_pair<BN, 1>(ia);
     }
     __syncwarp();
-  } else if (warp >= EPI_WARP0) {
-    // ------------------------------------------------------------------ epilogue warps
-    // the pair's work items are tile PAIRS; this CTA drains and stores its own tile of each pair (conv_tc_common.cuh)
-    conv_epilogue_warps<BN, true>(p, &tmOut, &tmPool, tmem_base, tfull0, tempty0, smem_out, s_head_w, s_head_b, first_pair, total_pairs,
-                                  pair_step, my_tile, num_chunks);
+  }
   }
   tc_fence_before();
   __syncthreads();

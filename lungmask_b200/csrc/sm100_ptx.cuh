@@ -65,16 +65,21 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 #ifndef LM_MBAR_SPIN_LIMIT
 #define LM_MBAR_SPIN_LIMIT (1u << 24)   // try_wait suspends ~1 us per failed try: ~10-20 s before trapping
 #endif
+// REGION: one copy of the out-of-line trap per register-allocation region of a kernel that uses setmaxnreg - ptxas gives
+// every region that calls a common subroutine the smallest register budget among them (measured: a shared trap routine
+// capped the epilogue warps at the producer's 96 registers).
+template <int REGION>
 static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
   printf("mbar_wait timeout: block %d thread %d bar 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
   __trap();
 }
 // The hot loop is try_wait only (the instruction itself suspends the thread until the phase flips or a
 // hardware time limit expires); the watchdog is an iteration count, so no clock reads sit on the wake-up path.
+template <int REGION = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > LM_MBAR_SPIN_LIMIT) mbar_timeout_trap(bar, parity);
+    if (++spins > LM_MBAR_SPIN_LIMIT) mbar_timeout_trap<REGION>(bar, parity);
   }
 }
 
@@ -253,6 +258,10 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
   lo = __uint_as_float(l);
 }
+
+// Register reallocation between warpgroups (setmaxnreg: all four warps of a warpgroup execute it together).
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---------------------------------------------------------------- CTA pairs (cluster of 2, tcgen05 cta_group::2)
 // Used by conv_tc_pair.cu.  In a cluster launch a shared::cta address is also a valid shared::cluster address of the

@@ -268,6 +268,9 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
     const double ctas = std::min<double>(num_sms, tiles / reps) * reps;
     printf("PROF  %-18s per k-block cycles: kernel %.0f | producer wait aempty %.0f bempty %.0f | mma wait tempty %.0f afull %.0f bfull %.0f issue %.0f | epi wait tfull %.0f drain %.0f, tile-epilogue per tile %.0f\n",
            L.name, pr[9] / kbs * 1.0 * 1, pr[0] / kbs, pr[1] / kbs, pr[2] / kbs, pr[3] / kbs, pr[4] / kbs, pr[5] / kbs, pr[6] / kbs, pr[7] / kbs, pr[8] / tiles);
+    if (!g_pair) printf("PROF2 %-18s issuer per k-block: first two k-steps %.0f | last two k-steps %.0f | commits %.0f | barrier waits %.0f | everything else %.0f\n",
+           L.name, pr[10] / kbs, pr[11] / kbs, pr[12] / kbs, (pr[2] + pr[3] + pr[4]) / kbs,
+           (double)pr[5] / kbs - (double)(pr[10] + pr[11] + pr[12] + pr[2] + pr[3] + pr[4]) / kbs);
     (void)ctas;
   }
 #endif
