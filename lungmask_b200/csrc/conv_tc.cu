@@ -61,6 +61,15 @@ __device__ unsigned long long g_conv_prof[16];
 #endif
 #include "conv_tc_common.cuh"
 
+#ifndef LM_TAP_UNROLL
+#define LM_TAP_UNROLL 1   // 1: the nine taps of a channel block are unrolled (compile-time descriptor offsets); 0: a loop
+#endif
+#if LM_TAP_UNROLL
+#define LM_TAP_PRAGMA _Pragma("unroll")
+#else
+#define LM_TAP_PRAGMA _Pragma("unroll 1")
+#endif
+
 namespace lm {
 namespace {
 
@@ -133,7 +142,7 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
       const uint32_t a_cb = a_base_lo + ab * (uint32_t)(A_BUF_BYTES >> 4);
       const uint32_t ab_cur = ab;
       const bool last_cb = (cb == g.num_cb - 1);
-#pragma unroll
+      LM_TAP_PRAGMA
       for (int tap = 0; tap < TAPS; ++tap) {
         // tap (dy, dx) = the same patch entered (dy * PATCH_W + dx) rows further (16-byte units: 8 per row)
         const uint32_t tap_off = (TAPS == 9) ? (uint32_t)(((tap / 3) * PATCH_W + (tap % 3)) * 8) : 0u;

@@ -15,6 +15,11 @@
 #ifndef LM_SETMAXNREG
 #define LM_SETMAXNREG 1
 #endif
+#ifndef LM_BN128_GROUPS
+// epilogue organisation of the BN = 128 kernel: 1 = all eight warps work on every tile (64 columns per thread);
+// 2 = two groups of four warps take alternate tiles (128 columns per thread, needs the setmaxnreg register budget)
+#define LM_BN128_GROUPS 1
+#endif
 #ifndef LM_REGS_LOW
 #define LM_REGS_LOW 88
 #define LM_REGS_HIGH 208
@@ -52,8 +57,8 @@ struct Cfg {
   // BN = 64: a thread can hold a full row (64 columns), so the warps form TWO GROUPS that take alternate tiles:
   // while one group runs the tile-end epilogue (BN, split, TMA stores - a third of a short 18-k-block tile), the
   // other already drains the next tile's chunks and the tensor pipe never waits for a free accumulator slot.
-  static constexpr int HALVES = (BN == 64) ? 1 : 2;
-  static constexpr int EGROUPS = (BN == 64) ? 2 : 1;
+  static constexpr int HALVES = (BN == 64 || LM_BN128_GROUPS == 2) ? 1 : 2;
+  static constexpr int EGROUPS = (BN == 64 || LM_BN128_GROUPS == 2) ? 2 : 1;
   // Everything lives in dynamic shared memory (declared __align__(1024): the swizzled tiles need it, and no static shared
   // memory means no alignment slack): activation patches | weight ring | output staging | per-channel constants |
   // mbarriers | TMEM base | head
@@ -108,9 +113,11 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
   uint32_t buf = 0;          // ring slot of the next chunk (all tiles, both groups, advance it)
   uint32_t phase_bits = 0;   // bit b: parity this group's next wait on slot b expects (its own barrier set)
   uint32_t tseq = 0;
-  float* cst = smem_const + (warp - EPI_WARP0) * CONST_WARP_FLOATS;   // this warp's bias | scale | shift (NC = 64 each)
+  // per-channel constants (bias | scale | shift, NC each): a private copy per warp when a thread holds 64 columns, one copy
+  // per group of four warps (filled together, two named barriers per tile) when it holds 128
+  static_assert(NC == 64 || (NC == 128 && EGROUPS == 2), "64 accumulator columns per thread, or 128 in two groups");
+  float* cst = smem_const + ((NC == 64) ? (warp - EPI_WARP0) * CONST_WARP_FLOATS : (int)egroup * 3 * NC);
   int const_n0 = -1;                                                  // channel block they belong to
-  static_assert(NC == 64, "one epilogue thread holds 64 accumulator columns");
   for (int item = first_item; item < total_items; item += item_step, ++tseq) {
     if (EGROUPS == 2 && (tseq & 1u) != egroup) { buf = (buf + (uint32_t)num_chunks) % NBUF; continue; }  // the other group's tile
     const TileCoord t = decode_tile(tile_of(item), n_tiles, tiles_x, tiles_img, BN);
@@ -124,8 +131,8 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       // LDG per lane, in flight while the tile's chunks are computed - and reads them back as broadcast LDS.128.
       const_n0 = t.n0;
       const int cb0 = t.n0 + half * NC;
-      __syncwarp();                                        // the previous tile's reads are done
-      {
+      if (NC == 64) {
+        __syncwarp();                                        // the previous tile's reads are done
         const int arr = lane >> 4, i4 = lane & 15;         // lanes 0-15: bias, 16-31: scale; then lanes 0-15: shift
         const float* src = arr == 0 ? p.bias : p.scale;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -136,8 +143,19 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
           if (p.shift) h = __ldg(reinterpret_cast<const float4*>(p.shift + cb0) + i4);
           reinterpret_cast<float4*>(cst)[32 + lane] = h;
         }
+        __syncwarp();
+      } else {
+        const int gt = (warp - EPI_WARP0 - 4 * (int)egroup) * 32 + lane;   // 0..127 inside the group
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)egroup) : "memory");   // the group's reads of the previous block are done
+        if (gt < 3 * (NC / 4)) {
+          const int arr = gt / (NC / 4), i4 = gt % (NC / 4);
+          const float* src = arr == 0 ? p.bias : (arr == 1 ? p.scale : p.shift);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (src) v = __ldg(reinterpret_cast<const float4*>(src + cb0) + i4);
+          reinterpret_cast<float4*>(cst)[gt] = v;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)egroup) : "memory");
       }
-      __syncwarp();
     }
     for (int c = 0; c < num_chunks; ++c) {
       { LM_PROF_T0(); mbar_wait<1>(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
@@ -146,30 +164,59 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       LM_PROF_T0();
       const uint32_t col0 = tmem_base + lane_base + buf * C::ACC_COLS + half * NC;
       const bool last_use = c >= num_chunks - NBUF;  // this slot is not written again in this tile
-      // all TMEM reads of this slot first, then hand the slot back BEFORE the register adds: the
-      // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
-      float v[NC];
-#pragma unroll
-      for (int j = 0; j < NC / 32; ++j) {
-        if (!(LM_EXP & 2) || last_use) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
-      }
-      if (last_use) {
-        float w[NC];
-#pragma unroll
-        for (int j = 0; j < NC / 32; ++j) tmem_ld32(col0 + BN + j * 32, w + j * 32);  // the slot's corrections, whole tile
-        tmem_ld_wait();
+      auto hand_back = [&]() {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
+      };
+      if (NC == 64) {
+        // all TMEM reads of this slot first, then hand the slot back BEFORE the register adds: the
+        // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
+        float v[64];
 #pragma unroll
-        for (int i = 0; i < NC; ++i) acc[i] = (acc[i] + v[i]) + w[i] * kLoUnscale;  // exact power-of-two rescale of hi*lo + lo*hi
+        for (int j = 0; j < 2; ++j) {
+          if (!(LM_EXP & 2) || last_use) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
+        }
+        if (last_use) {
+          float w[64];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tmem_ld32(col0 + BN + j * 32, w + j * 32);  // the slot's corrections, whole tile
+          tmem_ld_wait();
+          hand_back();
+#pragma unroll
+          for (int i = 0; i < 64; ++i) acc[i] = (acc[i] + v[i]) + w[i] * kLoUnscale;  // exact power-of-two rescale of hi*lo + lo*hi
+        } else {
+          tmem_ld_wait();
+          hand_back();
+#pragma unroll
+          for (int i = 0; i < 64; ++i) acc[i] += v[i];
+        }
       } else {
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
+        // 128 columns per thread: the same sums in the same order, read in 64-column pieces so that accumulators plus one
+        // piece fit the register budget; the slot goes back after the last piece has been read
+        constexpr int PIECES = NC / 64;
 #pragma unroll
-        for (int i = 0; i < NC; ++i) acc[i] += v[i];
+        for (int pc = 0; pc < PIECES; ++pc) {
+          float v[64];
+          tmem_ld32(col0 + pc * 64, v);
+          tmem_ld32(col0 + pc * 64 + 32, v + 32);
+          tmem_ld_wait();
+          if (pc == PIECES - 1 && !last_use) hand_back();
+#pragma unroll
+          for (int i = 0; i < 64; ++i) acc[pc * 64 + i] += v[i];
+        }
+        if (last_use) {
+#pragma unroll
+          for (int pc = 0; pc < PIECES; ++pc) {
+            float w[64];
+            tmem_ld32(col0 + BN + pc * 64, w);
+            tmem_ld32(col0 + BN + pc * 64 + 32, w + 32);
+            tmem_ld_wait();
+            if (pc == PIECES - 1) hand_back();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) acc[pc * 64 + i] = acc[pc * 64 + i] + w[i] * kLoUnscale;
+          }
+        }
       }
       if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(7);
       if (++buf == NBUF) buf = 0;

@@ -19,7 +19,7 @@ def test_cli_dicom_and_reoriented_nifti(tmp_path, models):
     from lungmask_b200 import LMInferer, io as lio
     from lungmask_b200.__main__ import main
     from oracle import synth
-    from tests.test_io import _write_dicom
+    from _dicom_writer import _write_dicom
 
     p = str(tmp_path / "w3.pth")
     torch.save(models[3], p)
