@@ -61,13 +61,13 @@ __device__ unsigned long long g_conv_prof[16];
 #endif
 #include "conv_tc_common.cuh"
 
-#ifndef LM_TAP_UNROLL
-#define LM_TAP_UNROLL 1   // 1: the nine taps of a channel block are unrolled (compile-time descriptor offsets); 0: a loop
-#endif
-#if LM_TAP_UNROLL
-#define LM_TAP_PRAGMA _Pragma("unroll")
-#else
-#define LM_TAP_PRAGMA _Pragma("unroll 1")
+#ifndef LM_TAP_LOOP
+// Layers whose tiles are ONE channel block deep (64 input channels: 9 k-blocks per tile) run the issue loop with the nine taps
+// as a real loop instead of unrolled: these are the layers whose epilogue warps are busy most of the time, and the unrolled
+// loop's 16 KB of straight-line code then competes with the epilogue's for instruction fetch - measured -22 % / -16 % on
+// down0.block3 / up3.block3+head, while the 18-k-block up3.block0 is 8 % FASTER unrolled (profiles/r02_call7_*).
+// 0 = always unrolled, 1 = this rule, 2 = always a loop.
+#define LM_TAP_LOOP 1
 #endif
 
 namespace lm {
@@ -101,7 +101,7 @@ struct IssueArgs {
 // of one k-block and the first MMA of the next must stay short.  The barrier waits and ring bookkeeping of k-block
 // i+1 (weight stage, activation buffer) are therefore executed in the MIDDLE of k-block i's MMA burst and the
 // burst's remaining MMAs then follow back to back with k-block i+1's first ones.
-template <int BN, int TAPS, bool DUAL>
+template <int BN, int TAPS, bool DUAL, bool UNROLL = true>
 __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
   using C = Cfg<BN>;
   constexpr uint32_t STAGES = C::STAGES, NBUF = C::NBUF;
@@ -142,7 +142,7 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
       const uint32_t a_cb = a_base_lo + ab * (uint32_t)(A_BUF_BYTES >> 4);
       const uint32_t ab_cur = ab;
       const bool last_cb = (cb == g.num_cb - 1);
-      LM_TAP_PRAGMA
+#pragma unroll(UNROLL ? TAPS : 1)
       for (int tap = 0; tap < TAPS; ++tap) {
         // tap (dy, dx) = the same patch entered (dy * PATCH_W + dx) rows further (16-byte units: 8 per row)
         const uint32_t tap_off = (TAPS == 9) ? (uint32_t)(((tap / 3) * PATCH_W + (tap % 3)) * 8) : 0u;
@@ -345,7 +345,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         ia.smem_a = smem_u32(smem); ia.smem_b = smem_u32(smem_b);
         ia.full0 = full0; ia.empty0 = empty0; ia.tfull0 = tfull0; ia.tempty0 = tempty0; ia.afull0 = afull0; ia.aempty0 = aempty0;
         if (dual_issue) { if (taps == 9) mma_issue_loop<BN, 9, true>(ia); else mma_issue_loop<BN, 1, true>(ia); }
-        else            { if (taps == 9) mma_issue_loop<BN, 9, false>(ia); else mma_issue_loop<BN, 1, false>(ia); }
+        else if (taps != 9) mma_issue_loop<BN, 1, false>(ia);
+        else if (LM_TAP_LOOP == 2 || (LM_TAP_LOOP == 1 && BN == 64 && num_cb == 1)) mma_issue_loop<BN, 9, false, false>(ia);
+        else mma_issue_loop<BN, 9, false, true>(ia);
       }
     }
     __syncwarp();

@@ -15,11 +15,6 @@
 #ifndef LM_SETMAXNREG
 #define LM_SETMAXNREG 1
 #endif
-#ifndef LM_BN128_GROUPS
-// epilogue organisation of the BN = 128 kernel: 1 = all eight warps work on every tile (64 columns per thread);
-// 2 = two groups of four warps take alternate tiles (128 columns per thread, needs the setmaxnreg register budget)
-#define LM_BN128_GROUPS 1
-#endif
 #ifndef LM_REGS_LOW
 #define LM_REGS_LOW 88
 #define LM_REGS_HIGH 208
@@ -57,8 +52,9 @@ struct Cfg {
   // BN = 64: a thread can hold a full row (64 columns), so the warps form TWO GROUPS that take alternate tiles:
   // while one group runs the tile-end epilogue (BN, split, TMA stores - a third of a short 18-k-block tile), the
   // other already drains the next tile's chunks and the tensor pipe never waits for a free accumulator slot.
-  static constexpr int HALVES = (BN == 64 || LM_BN128_GROUPS == 2) ? 1 : 2;
-  static constexpr int EGROUPS = (BN == 64 || LM_BN128_GROUPS == 2) ? 2 : 1;
+  static constexpr int HALVES = (BN == 64) ? 1 : 2;
+  static constexpr int EGROUPS = (BN == 64) ? 2 : 1;   // (two groups of 128 columns per thread for BN = 128: measured, no gain -
+                                                       //  profiles/r02_call7_*: the tile-end latency per tile doubles)
   // Everything lives in dynamic shared memory (declared __align__(1024): the swizzled tiles need it, and no static shared
   // memory means no alignment slack): activation patches | weight ring | output staging | per-channel constants |
   // mbarriers | TMEM base | head
@@ -113,10 +109,8 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
   uint32_t buf = 0;          // ring slot of the next chunk (all tiles, both groups, advance it)
   uint32_t phase_bits = 0;   // bit b: parity this group's next wait on slot b expects (its own barrier set)
   uint32_t tseq = 0;
-  // per-channel constants (bias | scale | shift, NC each): a private copy per warp when a thread holds 64 columns, one copy
-  // per group of four warps (filled together, two named barriers per tile) when it holds 128
-  static_assert(NC == 64 || (NC == 128 && EGROUPS == 2), "64 accumulator columns per thread, or 128 in two groups");
-  float* cst = smem_const + ((NC == 64) ? (warp - EPI_WARP0) * CONST_WARP_FLOATS : (int)egroup * 3 * NC);
+  static_assert(NC == 64, "one epilogue thread holds 64 accumulator columns");
+  float* cst = smem_const + (warp - EPI_WARP0) * CONST_WARP_FLOATS;   // this warp's bias | scale | shift (64 floats each)
   int const_n0 = -1;                                                  // channel block they belong to
   for (int item = first_item; item < total_items; item += item_step, ++tseq) {
     if (EGROUPS == 2 && (tseq & 1u) != egroup) { buf = (buf + (uint32_t)num_chunks) % NBUF; continue; }  // the other group's tile
@@ -131,31 +125,23 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
       // LDG per lane, in flight while the tile's chunks are computed - and reads them back as broadcast LDS.128.
       const_n0 = t.n0;
       const int cb0 = t.n0 + half * NC;
-      if (NC == 64) {
-        __syncwarp();                                        // the previous tile's reads are done
-        const int arr = lane >> 4, i4 = lane & 15;         // lanes 0-15: bias, 16-31: scale; then lanes 0-15: shift
-        const float* src = arr == 0 ? p.bias : p.scale;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src) v = __ldg(reinterpret_cast<const float4*>(src + cb0) + i4);
-        reinterpret_cast<float4*>(cst)[lane] = v;
-        if (lane < 16) {
-          float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.shift) h = __ldg(reinterpret_cast<const float4*>(p.shift + cb0) + i4);
-          reinterpret_cast<float4*>(cst)[32 + lane] = h;
-        }
-        __syncwarp();
-      } else {
-        const int gt = (warp - EPI_WARP0 - 4 * (int)egroup) * 32 + lane;   // 0..127 inside the group
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)egroup) : "memory");   // the group's reads of the previous block are done
-        if (gt < 3 * (NC / 4)) {
-          const int arr = gt / (NC / 4), i4 = gt % (NC / 4);
-          const float* src = arr == 0 ? p.bias : (arr == 1 ? p.scale : p.shift);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (src) v = __ldg(reinterpret_cast<const float4*>(src + cb0) + i4);
-          reinterpret_cast<float4*>(cst)[gt] = v;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)egroup) : "memory");
+      // The stored planes hold y * out_scale with y = relu(..) * scale + shift: the power-of-two factor goes into the copies
+      // of scale and shift (scaling by 2^k commutes with every rounding involved).  The head consumes y itself.
+      const float cscale = (p.mode == kModeHead) ? 1.f : p.out_scale;
+      __syncwarp();                                        // the previous tile's reads are done
+      const int arr = lane >> 4, i4 = lane & 15;         // lanes 0-15: bias, 16-31: scale; then lanes 0-15: shift
+      const float* src = arr == 0 ? p.bias : p.scale;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) v = __ldg(reinterpret_cast<const float4*>(src + cb0) + i4);
+      if (arr == 1) { v.x *= cscale; v.y *= cscale; v.z *= cscale; v.w *= cscale; }
+      reinterpret_cast<float4*>(cst)[lane] = v;
+      if (lane < 16) {
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.shift) h = __ldg(reinterpret_cast<const float4*>(p.shift + cb0) + i4);
+        h.x *= cscale; h.y *= cscale; h.z *= cscale; h.w *= cscale;
+        reinterpret_cast<float4*>(cst)[32 + lane] = h;
       }
+      __syncwarp();
     }
     for (int c = 0; c < num_chunks; ++c) {
       { LM_PROF_T0(); mbar_wait<1>(tfull_g + 8 * buf, (phase_bits >> buf) & 1u); if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(6); }
@@ -169,54 +155,26 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
         __syncwarp();
         if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty0 + 8 * buf); else mbar_arrive(tempty0 + 8 * buf); }
       };
-      if (NC == 64) {
-        // all TMEM reads of this slot first, then hand the slot back BEFORE the register adds: the
-        // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
-        float v[64];
+      // all TMEM reads of this slot first, then hand the slot back BEFORE the register adds: the
+      // tensor core's next chunk on this slot does not have to wait for the fp32 accumulation
+      float v[64];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (!(LM_EXP & 2) || last_use) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
-        }
-        if (last_use) {
-          float w[64];
+      for (int j = 0; j < 2; ++j) {
+        if (!(LM_EXP & 2) || last_use) tmem_ld32(col0 + j * 32, v + j * 32);   // hi*hi partial sums of this chunk
+      }
+      if (last_use) {
+        float w[64];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) tmem_ld32(col0 + BN + j * 32, w + j * 32);  // the slot's corrections, whole tile
-          tmem_ld_wait();
-          hand_back();
+        for (int j = 0; j < 2; ++j) tmem_ld32(col0 + BN + j * 32, w + j * 32);  // the slot's corrections, whole tile
+        tmem_ld_wait();
+        hand_back();
 #pragma unroll
-          for (int i = 0; i < 64; ++i) acc[i] = (acc[i] + v[i]) + w[i] * kLoUnscale;  // exact power-of-two rescale of hi*lo + lo*hi
-        } else {
-          tmem_ld_wait();
-          hand_back();
-#pragma unroll
-          for (int i = 0; i < 64; ++i) acc[i] += v[i];
-        }
+        for (int i = 0; i < 64; ++i) acc[i] = (acc[i] + v[i]) + w[i] * kLoUnscale;  // exact power-of-two rescale of hi*lo + lo*hi
       } else {
-        // 128 columns per thread: the same sums in the same order, read in 64-column pieces so that accumulators plus one
-        // piece fit the register budget; the slot goes back after the last piece has been read
-        constexpr int PIECES = NC / 64;
+        tmem_ld_wait();
+        hand_back();
 #pragma unroll
-        for (int pc = 0; pc < PIECES; ++pc) {
-          float v[64];
-          tmem_ld32(col0 + pc * 64, v);
-          tmem_ld32(col0 + pc * 64 + 32, v + 32);
-          tmem_ld_wait();
-          if (pc == PIECES - 1 && !last_use) hand_back();
-#pragma unroll
-          for (int i = 0; i < 64; ++i) acc[pc * 64 + i] += v[i];
-        }
-        if (last_use) {
-#pragma unroll
-          for (int pc = 0; pc < PIECES; ++pc) {
-            float w[64];
-            tmem_ld32(col0 + BN + pc * 64, w);
-            tmem_ld32(col0 + BN + pc * 64 + 32, w + 32);
-            tmem_ld_wait();
-            if (pc == PIECES - 1) hand_back();
-#pragma unroll
-            for (int i = 0; i < 64; ++i) acc[pc * 64 + i] = acc[pc * 64 + i] + w[i] * kLoUnscale;
-          }
-        }
+        for (int i = 0; i < 64; ++i) acc[i] += v[i];
       }
       if (warp == EPI_WARP0 && lane == 0) LM_PROF_ADD(7);
       if (++buf == NBUF) buf = 0;
@@ -253,22 +211,18 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
                      : "memory");
       }
     };
-    // one 128-byte row of operand-format channels (BK of them) of plane `plane`, from fp32 values
-    auto pack_row = [&](const float* src, int plane, uint32_t* v) {
+    // one 128-byte row of operand-format channels (BK of them) per plane, from fp32 values: both planes in one pass
+    auto pack_rows = [&](const float* src, uint32_t* vh, uint32_t* vl) {
 #if LM_OPERAND_F16
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        __half h0, l0, h1, l1;
-        split_f16(src[2 * i], h0, l0);
-        split_f16(src[2 * i + 1], h1, l1);
-        v[i] = plane ? pack_half2(l0, l1) : pack_half2(h0, h1);
-      }
+      for (int i = 0; i < 32; ++i) split_f16x2(src[2 * i], src[2 * i + 1], vh[i], vl[i]);
 #else
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float hi, lo;
         split_tf32(src[i], hi, lo);
-        v[i] = __float_as_uint(plane ? lo : hi);
+        vh[i] = __float_as_uint(hi);
+        vl[i] = __float_as_uint(lo);
       }
 #endif
     };
@@ -383,11 +337,7 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
         }
         p.labels[((size_t)t.n * p.H + y) * p.W + x] = (uint8_t)best;
       } else {
-        {  // the stored planes hold y * out_scale
-          const float oscale = p.out_scale;
-#pragma unroll
-          for (int i = 0; i < NC; ++i) acc[i] = __fmul_rn(acc[i], oscale);
-        }
+        // (the stored planes hold y * out_scale: the power-of-two factor is already in the scale / shift copies)
 #if LM_OPERAND_F16
         {  // fp16 saturates: report instead of storing inf (the engine lowers out_scale and runs again)
           bool ovf = false;
@@ -398,10 +348,11 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
 #endif
 #pragma unroll
         for (int g = 0; g < NC / BK; ++g) {
+          uint32_t vh[32], vl[32];
+          pack_rows(acc + g * BK, vh, vl);
 #pragma unroll
           for (int plane = 0; plane < 2; ++plane) {
-            uint32_t v[32];
-            pack_row(acc + g * BK, plane, v);
+            const uint32_t* v = plane ? vl : vh;
 #if LM_TMA_STORES == 1
             round_begin();
             stage_row((uint32_t)lane, v);
@@ -428,10 +379,11 @@ __device__ __forceinline__ void conv_epilogue_warps(const ConvParams& p, const C
               s = s + __shfl_xor_sync(0xffffffffu, s, 8);
               pv[i] = s * 0.25f;
             }
+            uint32_t vh[32], vl[32];
+            pack_rows(pv, vh, vl);
 #pragma unroll
             for (int plane = 0; plane < 2; ++plane) {
-              uint32_t v[32];
-              pack_row(pv, plane, v);
+              const uint32_t* v = plane ? vl : vh;
 #if LM_TMA_STORES == 1
               round_begin();
               if (writer) stage_row(prow, v);
