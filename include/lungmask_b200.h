@@ -169,8 +169,9 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * accumulated inside the tensor core between fp32 round-to-nearest adds; sets both layer classes),
  * "chunk_kb_wide" (the same for the layers with >= 128 output channels only; defaults: 1 for the 64-channel
  * layers, 2 for the wide ones), "dual_issue" (0/1: a second MMA-issuing thread per CTA on alternate chunks;
- * default 0), "cta_pairs" (0/1: the experimental cta_group::2 convolution kernel; default 0),
- * "stem_v2" (0/1: the experimental register-resident stem kernel; default 0),
+ * default 0), "cta_pairs" (0/1: the cta_group::2 convolution kernel: validated, on par, default 0),
+ * "weight_mcast" (0 / 2: clusters of two CTAs share every weight stage through TMA multicast),
+ * "stem_v2" (0 = first stem kernel, 1 = register-resident, 2 = shared-memory tile, the default),
  * "graphs" (1, default: a volume's forward - every wave's ~26 launches - is captured once as a CUDA graph and replayed;
  * 0: every kernel is launched individually; per-launch convolution timing and score taps always launch individually),
  * "upsample_v2" (0/1: cell-centred bilinear upsample kernel),

@@ -101,7 +101,7 @@ struct IssueArgs {
 // of one k-block and the first MMA of the next must stay short.  The barrier waits and ring bookkeeping of k-block
 // i+1 (weight stage, activation buffer) are therefore executed in the MIDDLE of k-block i's MMA burst and the
 // burst's remaining MMAs then follow back to back with k-block i+1's first ones.
-template <int BN, int TAPS, bool DUAL, bool UNROLL = true>
+template <int BN, int TAPS, bool DUAL, bool UNROLL = true, int MC = 1>
 __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
   using C = Cfg<BN>;
   constexpr uint32_t STAGES = C::STAGES, NBUF = C::NBUF;
@@ -198,7 +198,8 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
           LM_PROF_ADD(11);   // the other two k-steps
           {
             LM_PROF_T0();
-            umma_commit(g.empty0 + 8 * s_cur);           // weight stage consumed (only this issuer read it)
+            if (MC > 1) umma_commit_mcast(g.empty0 + 8 * s_cur, (uint16_t)((1u << MC) - 1u));  // ... in every CTA of the cluster
+            else umma_commit(g.empty0 + 8 * s_cur);      // weight stage consumed (only this issuer read it)
             if (chunk_end) umma_commit(tfull_cur);       // chunk complete -> the tile's epilogue group may drain it
             LM_PROF_ADD(12);
           }
@@ -216,11 +217,17 @@ __device__ __forceinline__ void mma_issue_loop(const IssueArgs& g) {
 #endif
 }
 
-template <int BN>
+// MC = 1: independent CTAs.  MC = 2: weight multicast - the two CTAs of a cluster work on two pixel tiles of the SAME
+// output-channel block in lock step per weight stage: CTA r loads plane r (hi / lo) of every stage with a TMA multicast
+// into both CTAs' rings, both CTAs' full barriers count the bytes of both loads, a stage is free again when BOTH issuers'
+// MMAs on it have retired (multicast commit on both CTAs' empty barriers, count 2).  Half the L2 -> SM weight bytes per MAC:
+// the deep layers sit at the chip's L2 throughput cap.  Everything else - activations, MMAs
+// (cta_group::1), epilogue - is per CTA and unchanged.
+template <int BN, int MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
-               const __grid_constant__ CUtensorMap tmPool, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBX,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmPool, const ConvParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   constexpr int NBUF = C::NBUF;
@@ -252,10 +259,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int num_chunks = (num_kb + chunk_kb - 1) / chunk_kb;
   // Two MMA-issuing warps take alternate chunks unless a chunk spans a whole weight ring (then the issuer that
   // does not own it could fall a full ring behind and its phase bit would alias); see mma_issue_loop.
-  const bool dual_issue = p.dual_issue && (chunk_kb <= STAGES - 1) && (num_chunks >= 2);
+  const bool dual_issue = (MC == 1) && p.dual_issue && (chunk_kb <= STAGES - 1) && (num_chunks >= 2);
+  // work items: tiles (MC = 1) or clusters' tile groups (MC pixel tiles of one channel block, this CTA takes pixel tile
+  // MC * group + rank); every CTA of a cluster walks the same item sequence
+  const uint32_t rank = (MC > 1) ? cluster_ctarank() : 0u;
+  const int first_item = (int)blockIdx.x / MC, item_step = (int)gridDim.x / MC, total_items = total_tiles / MC;
+  auto tile_of = [&](int q) { if (MC == 1) return q; const int mtp = q / n_tiles; return (MC * mtp + (int)rank) * n_tiles + (q - mtp * n_tiles); };
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, MC); }
     for (int s = 0; s < NUM_A_BUFS; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, dual_issue ? 2 : 1); }
     for (int b = 0; b < EGROUPS * NBUF; ++b) mbar_init(tfull0 + 8 * b, 1);
     for (int b = 0; b < NBUF; ++b) mbar_init(tempty0 + 8 * b, NUM_EPI_THREADS / 32 / EGROUPS);
@@ -270,6 +282,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (MC > 1) cluster_sync_all();  // the peer's barriers are initialised before any multicast load / commit signals them
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 #ifdef LM_CONV_PROFILE
@@ -287,10 +300,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     setmaxnreg_inc<LM_REGS_HIGH>();
 #endif
     // ------------------------------------------------------------------ epilogue warps
-    conv_epilogue_warps<BN, false>(p, &tmOut, &tmPool, tmem_base, tfull0, tempty0, smem_out, reinterpret_cast<float*>(smem + C::OFF_CONST), s_head_w, s_head_b, (int)blockIdx.x,
-                                   total_tiles, (int)gridDim.x, [](int item) { return item; }, num_chunks);
+    conv_epilogue_warps<BN, false>(p, &tmOut, &tmPool, tmem_base, tfull0, tempty0, smem_out, reinterpret_cast<float*>(smem + C::OFF_CONST), s_head_w, s_head_b, first_item,
+                                   total_items, item_step, tile_of, num_chunks);
     tc_fence_before();
     __syncthreads();   // the kernel's last barrier (the other warps arrive at it from their own branch)
+    if (MC > 1) cluster_sync_all();
     return;
   } else {
 #if LM_SETMAXNREG
@@ -300,7 +314,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // ------------------------------------------------------------------ TMA producer
     uint32_t s = 0, ph = 0, ab = 0, aph = 0;
     const uint32_t a_tx = 2u * (uint32_t)a_plane_bytes;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int item = first_item; item < total_items; item += item_step) {
+      const int tile = tile_of(item);
       const TileCoord t = decode_tile(tile, n_tiles, tiles_x, tiles_img, BN);
       int c = 0;
       for (int cb = 0; cb < num_cb; ++cb, c += BK) {
@@ -319,6 +334,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (elect_one()) {
             if ((LM_EXP & 32) && (tile != (int)blockIdx.x || cb > 0 || tap >= STAGES)) {
               mbar_arrive(full0 + 8 * s);  // ablation: reuse whatever the stage holds
+            } else if (MC > 1) {
+              // this CTA's plane of the stage, into both CTAs' rings; the local barrier expects both planes
+              mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
+              tma_load_4d_mcast(smem_u32(smem_b) + s * C::STAGE_BYTES + rank * (uint32_t)C::B_PLANE_BYTES, &tmBX, full0 + 8 * s, c, t.n0, tap,
+                                (int)rank, (uint16_t)((1u << MC) - 1u));
             } else {
               mbar_arrive_expect_tx(full0 + 8 * s, C::STAGE_BYTES);
               tma_load_4d(smem_u32(smem_b) + s * C::STAGE_BYTES, &tmB, full0 + 8 * s, c, t.n0, tap, 0);
@@ -327,6 +347,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
+      }
+    }
+    if (MC > 1) {
+      // cluster tail: the releases of the last STAGES k-blocks (commits from BOTH CTAs' issuers) have landed on this CTA's
+      // barriers before it may exit - no signal is left in flight towards shared memory that a later CTA could own
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -340,14 +368,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const uint32_t me = (warp == 3) ? 1u : 0u;
       if (dual_issue || me == 0u) {
         IssueArgs ia;
-        ia.me = me; ia.first_tile = (int)blockIdx.x; ia.total_tiles = total_tiles; ia.tile_step = (int)gridDim.x;
+        ia.me = me; ia.first_tile = first_item; ia.total_tiles = total_items; ia.tile_step = item_step;
         ia.num_cb = num_cb; ia.chunk_kb = chunk_kb; ia.tmem_base = tmem_base;
         ia.smem_a = smem_u32(smem); ia.smem_b = smem_u32(smem_b);
         ia.full0 = full0; ia.empty0 = empty0; ia.tfull0 = tfull0; ia.tempty0 = tempty0; ia.afull0 = afull0; ia.aempty0 = aempty0;
         if (dual_issue) { if (taps == 9) mma_issue_loop<BN, 9, true>(ia); else mma_issue_loop<BN, 1, true>(ia); }
-        else if (taps != 9) mma_issue_loop<BN, 1, false>(ia);
-        else if (LM_TAP_LOOP == 2 || (LM_TAP_LOOP == 1 && BN == 64 && num_cb == 1)) mma_issue_loop<BN, 9, false, false>(ia);
-        else mma_issue_loop<BN, 9, false, true>(ia);
+        else if (taps != 9) mma_issue_loop<BN, 1, false, true, MC>(ia);
+        else if (LM_TAP_LOOP == 2 || (LM_TAP_LOOP == 1 && BN == 64 && num_cb == 1)) mma_issue_loop<BN, 9, false, false, MC>(ia);
+        else mma_issue_loop<BN, 9, false, true, MC>(ia);
       }
     }
     __syncwarp();
@@ -358,6 +386,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #ifdef LM_CONV_PROFILE
   if (threadIdx.x == 0) atomicAdd(&g_conv_prof[9], (unsigned long long)(clock64() - prof_kernel_t0));
 #endif
+  if (MC > 1) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -461,22 +490,38 @@ int make_conv_maps(ConvMaps* maps, const void* src0, const void* src1, const voi
   return 0;
 }
 
-template <int BN>
+template <int BN, int MC>
 static int launch_impl(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   static std::atomic<unsigned long long> attr_set_mask{0ull};  // engines of several host threads may launch concurrently
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
   if (!((attr_set_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg<BN>::DYN_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set_mask.fetch_or(1ull << dev, std::memory_order_release);
   }
   const int total = p.N * (p.H / TILE_H) * (p.W / TILE_W) * (p.Cout / BN);
-  const int grid = total < num_sms ? total : num_sms;
-  conv_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::DYN_SMEM, stream>>>(maps.a0, maps.a1, maps.b, maps.out, maps.pool, p);
-  return (int)cudaGetLastError();
+  if (MC == 1) {
+    const int grid = total < num_sms ? total : num_sms;
+    conv_tc_kernel<BN, 1><<<grid, NUM_THREADS, Cfg<BN>::DYN_SMEM, stream>>>(maps.a0, maps.a1, maps.b, maps.bx, maps.out, maps.pool, p);
+    return (int)cudaGetLastError();
+  }
+  // clusters of MC CTAs: MC pixel tiles of one channel block per work item (every level has an even number of pixel tiles)
+  const int groups = total / MC, sm_groups = num_sms / MC;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(MC * (groups < sm_groups ? groups : sm_groups)), 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg<BN>::DYN_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, MC>, maps.a0, maps.a1, maps.b, maps.bx, maps.out, maps.pool, p);
+  return (int)(e != cudaSuccess ? e : cudaGetLastError());
 }
 
 #ifdef LM_CONV_PROFILE
@@ -487,16 +532,20 @@ void conv_prof_read(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_conv_
 // Sets the kernels' > 48 KB dynamic shared-memory opt-in on the current device (lm_create calls it, so that no launch -
 // in particular none inside a CUDA-graph capture - has to).
 int conv_tc_prepare() {
-  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::DYN_SMEM);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::DYN_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::DYN_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::DYN_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::DYN_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::DYN_SMEM);
   return (int)e;
 }
 
 int launch_conv_tc(const ConvMaps& maps, const ConvParams& p, int num_sms, cudaStream_t stream) {
   if (p.mode == kModeHead && (p.Cout != 64 || p.K > MAX_CLASSES)) return -4;
   if (p.chunk_kb < 1) return -5;
-  return conv_tile_n(p) == 128 ? launch_impl<128>(maps, p, num_sms, stream)
-                               : launch_impl<64>(maps, p, num_sms, stream);
+  if (p.weight_mcast == 2)
+    return conv_tile_n(p) == 128 ? launch_impl<128, 2>(maps, p, num_sms, stream) : launch_impl<64, 2>(maps, p, num_sms, stream);
+  return conv_tile_n(p) == 128 ? launch_impl<128, 1>(maps, p, num_sms, stream)
+                               : launch_impl<64, 1>(maps, p, num_sms, stream);
 }
 
 }  // namespace lm

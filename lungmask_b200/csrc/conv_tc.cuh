@@ -54,6 +54,7 @@ struct ConvParams {
   int chunk_kb;       // k-blocks (kBK channels x 1 tap) accumulated inside the tensor core before the
                       // partial sum is added, round-to-nearest, into fp32 registers
   int dual_issue;     // 1: two MMA-issuing threads take alternate chunks (0: one issuer)
+  int weight_mcast;   // 2: clusters of two CTAs share every weight stage through TMA multicast (conv_tc.cu, MC = 2); 0 / 1: off
   int tile_n;         // output-channel tile: 0 = conv_tile_n(Cout); 64 forces the BN = 64 kernel (two epilogue groups on
                       // alternate tiles) for a layer with Cout >= 128 - must be set before make_conv_maps
   const float* bias;  // [Cout]

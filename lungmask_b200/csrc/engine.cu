@@ -200,6 +200,7 @@ struct lm_engine {
   int64_t graph_launches = 0, graph_hits = 0;
   unsigned bn64_mask = 0; // bit i: layer i of LAYERS uses BN = 64 output-channel tiles although Cout >= 128 (read at lm_load_weights)
   int dual_issue = 0;     // 1: two MMA-issuing threads per CTA on alternate chunks (conv_tc.cu)
+  int weight_mcast = 0;   // 2: clusters of two CTAs share each weight stage through TMA multicast (conv_tc.cu, MC = 2)
   int cta_pairs = 0;      // 1: the cta_group::2 kernel (conv_tc_pair.cu): bit-identical on hardware, but slower than one CTA per tile
                           //    so far (r02: 14.3 vs 8.7 ms per 37-slice wave, profiles/r02_*) - opt-in
   int stem_v2 = 2;        // stem kernel version: 0 stem_kernel, 1 stem_kernel_v2 - weights in registers, 4-pixel quads
@@ -270,6 +271,7 @@ int forward_batch(lm_engine* e, Slot& s, const void* d_in, bool in_f32, int n, u
     p.in_unscale = 1.f / (s.act_scale[L.src0] * s.lw[i].w_scale);   // src1 (virtual concat) shares src0's scale group
     p.out_scale = (L.mode == kModeReluBn || L.mode == kModeReluBnPool) ? s.act_scale[L.dst] : 1.f;
     p.dual_issue = e->dual_issue;
+    p.weight_mcast = (e->weight_mcast == 2 && s.maps[i].pair_ok) ? 2 : 0;
     if (p.mode == kModeHead) { p.labels = d_labels; p.scores = d_scores; }
     if (time_convs) {
       if (e->ev_used + 2 > e->ev_pool.size()) {
@@ -621,6 +623,7 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = e->chunk_kb_wide = v; }
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
+  if (const char* c = getenv("LM_WEIGHT_MCAST")) e->weight_mcast = atoi(c);
   if (const char* c = getenv("LM_GRAPHS")) e->use_graphs = atoi(c) != 0;
   if (const char* c = getenv("LM_BN64_MASK")) e->bn64_mask = (unsigned)strtoul(c, nullptr, 0);
   if (const char* c = getenv("LM_STEM_V2")) { const int v = atoi(c); e->stem_v2 = v < 0 ? 0 : (v > 2 ? 2 : v); }
@@ -1229,6 +1232,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "chunk_kb")) { if (value < 1) return fail(-1, "chunk_kb must be >= 1"); e->chunk_kb = e->chunk_kb_wide = value; return 0; }
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
+  if (!strcmp(key, "weight_mcast")) { if (value != 0 && value != 2) return fail(-1, "weight_mcast must be 0 or 2"); e->weight_mcast = value; return 0; }
   if (!strcmp(key, "stem_v2")) { if (value < 0 || value > 2) return fail(-1, "stem_v2 must be 0, 1 or 2"); e->stem_v2 = value; return 0; }
   if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value != 0; return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }

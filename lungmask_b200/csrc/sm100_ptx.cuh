@@ -112,6 +112,17 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// the same load delivered to the same shared-memory offset of every CTA in `cta_mask` (one L2 read, fanned out on the way to
+// the SMs); each destination CTA's mbarrier at the offset of `bar` receives the complete_tx
+__device__ __forceinline__ void tma_load_4d_mcast(uint32_t dst, const CUtensorMap* m, uint32_t bar,
+                                                  int c0, int c1, int c2, int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
                                             int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -161,6 +172,12 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    bar)
+               : "memory");
+}
+// the same arrive on the mbarrier at this offset in every CTA of `cta_mask` (weight stages shared by a cluster)
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
                : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, fp32 accumulate. Single-thread issue.

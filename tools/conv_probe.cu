@@ -2,7 +2,7 @@
 // procedurally generated data (every element is a hash of its index, so the host can evaluate any
 // output pixel without holding the tensors), then times the 22 tensor-core layers of the U-Net at a
 // given batch. Test infrastructure only.
-//   usage: conv_probe [batch=8] [chunk_kb=4] [timing_only=0] [dual_issue=0] [cta_pairs=0]
+//   usage: conv_probe [batch=8] [chunk_kb=4] [timing_only=0] [dual_issue=0] [cta_pairs=0] [reps=3] [bn64_mask=0] [weight_mcast=0]
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -106,7 +106,7 @@ static float h_param(uint32_t seed, int c, int kind, bool ints) {
   return kind == 1 ? 1.0f + 0.3f * g : 0.2f * g;
 }
 
-static int g_dual = 0, g_pair = 0, g_tile_n = 0;   // g_tile_n: forced output-channel tile of the layer being run (0 = auto)
+static int g_dual = 0, g_pair = 0, g_mcast = 0, g_tile_n = 0;   // g_tile_n: forced output-channel tile of the layer being run (0 = auto)
 static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool check, bool ints, int reps) {
   const int Cin = L.C0 + L.C1;
   const float wscale = 1.0f / sqrtf((float)Cin * L.taps) * 1.7f;
@@ -143,7 +143,7 @@ static double run_layer(const Layer& L, int N, int chunk_kb, int num_sms, bool c
 
   ConvParams p{};
   p.N = N; p.H = L.H; p.W = L.W; p.C0 = L.C0; p.C1 = L.C1; p.Cout = L.Cout; p.taps = L.taps; p.mode = L.mode;
-  p.chunk_kb = chunk_kb; p.dual_issue = g_dual; p.tile_n = g_tile_n; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
+  p.chunk_kb = chunk_kb; p.dual_issue = g_dual; p.weight_mcast = g_mcast; p.tile_n = g_tile_n; p.bias = b.bias; p.scale = b.scale; p.shift = b.shift; p.out = b.out; p.out_pool = b.pool;
   p.head_w = b.hw; p.head_b = b.hb; p.K = L.K; p.labels = b.labels; p.scores = b.scores; p.range_flag = b.range_flag;
   p.in_unscale = 1.f; p.out_scale = 1.f;
   ConvMaps maps;
@@ -291,9 +291,10 @@ int main(int argc, char** argv) {
   g_pair = argc > 5 ? atoi(argv[5]) : 0;
   const int reps = argc > 6 ? atoi(argv[6]) : 3;   // timed repetitions per network layer (0: one untimed launch per layer, for ncu)
   const unsigned bn64_mask = argc > 7 ? (unsigned)strtoul(argv[7], nullptr, 0) : 0u;   // network layers (bit i) forced to BN = 64 tiles
+  g_mcast = argc > 8 ? atoi(argv[8]) : 0;   // 2: weight stages multicast across clusters of two CTAs
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
-  printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d cta_pairs %d\n", prop.name, sms, batch, chunk, g_dual, g_pair);
+  printf("device %s SMs %d; batch %d chunk_kb %d dual_issue %d cta_pairs %d weight_mcast %d\n", prop.name, sms, batch, chunk, g_dual, g_pair, g_mcast);
   if (!timing_only) {
     const Layer small[] = {
         {"ints 1tile", 16, 8, kBK, 0, 64, 9, kModeReluBn, 0},
