@@ -19,6 +19,14 @@
 #define LM_REGS_LOW 88
 #define LM_REGS_HIGH 208
 #endif
+#ifndef LM_TAP_LOOP
+// Layers whose tiles are ONE channel block deep (64 input channels: 9 k-blocks per tile) run the issue loop with the nine taps
+// as a real loop instead of unrolled: these are the layers whose epilogue warps are busy most of the time, and the unrolled
+// loop's 16 KB of straight-line code then competes with the epilogue's for instruction fetch - measured -22 % / -16 % on
+// down0.block3 / up3.block3+head, while the 18-k-block up3.block0 is 8 % FASTER unrolled (profiles/r02_call7_*).
+// 0 = always unrolled, 1 = this rule, 2 = always a loop.
+#define LM_TAP_LOOP 1
+#endif
 #include "conv_tc.cuh"
 #include "sm100_ptx.cuh"
 

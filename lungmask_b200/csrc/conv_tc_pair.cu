@@ -61,7 +61,7 @@ struct IssueArgs {
 
 // The MMA issue loop of the pair's leader (one elected lane): conv_tc.cu's mma_issue_loop<BN, TAPS, false> with
 // cta_group::2 instructions, the X / Y / W weight-stage layout and multicast commits.
-template <int BN, int TAPS>
+template <int BN, int TAPS, bool UNROLL = true>
 __device__ __forceinline__ void mma_issue_loop_pair(const IssueArgs& g) {
   using C = Cfg<BN>;
   constexpr uint32_t STAGES = C::STAGES, NBUF = C::NBUF;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void mma_issue_loop_pair(const IssueArgs& g) {
       const uint32_t a_cb = a_base_lo + ab * (uint32_t)(A_BUF_BYTES >> 4);
       const uint32_t ab_cur = ab;
       const bool last_cb = (cb == g.num_cb - 1);
-#pragma unroll
+#pragma unroll(UNROLL ? TAPS : 1)
       for (int tap = 0; tap < TAPS; ++tap) {
         const uint32_t tap_off = (TAPS == 9) ? (uint32_t)(((tap / 3) * PATCH_W + (tap % 3)) * 8) : 0u;
         const uint32_t buf = gc % NBUF;
@@ -272,7 +272,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       ia.num_cb = num_cb; ia.chunk_kb = chunk_kb; ia.tmem_base = tmem_base;
       ia.smem_a = smem_u32(smem); ia.smem_b = smem_u32(smem_b);
       ia.full0 = full0; ia.empty0 = empty0; ia.tfull0 = tfull0; ia.tempty0 = tempty0; ia.afull0 = afull0; ia.aempty0 = aempty0;
-      if (taps == 9) mma_issue_loop_pair<BN, 9>(ia); else mma_issue_loop_pair<BN, 1>(ia);
+      if (taps != 9) mma_issue_loop_pair<BN, 1>(ia);
+      else if (LM_TAP_LOOP == 2 || (LM_TAP_LOOP == 1 && BN == 64 && num_cb == 1)) mma_issue_loop_pair<BN, 9, false>(ia);   // conv_tc_common.cuh
+      else mma_issue_loop_pair<BN, 9, true>(ia);
     }
     __syncwarp();
   }

@@ -23,11 +23,7 @@ __device__ __forceinline__ void split_store(const float* v, op_t* hi_dst, op_t* 
   uint32_t* pl = &l.x;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    __half h0, l0, h1, l1;
-    split_f16(v[2 * e], h0, l0);
-    split_f16(v[2 * e + 1], h1, l1);
-    ph[e] = pack_half2(h0, h1);
-    pl[e] = pack_half2(l0, l1);
+    split_f16x2(v[2 * e], v[2 * e + 1], ph[e], pl[e]);   // packed conversions: the roundings of split_f16, two values at a time
     ovf |= !(fabsf(v[2 * e]) <= kOpMax) | !(fabsf(v[2 * e + 1]) <= kOpMax);
   }
 #else

@@ -78,3 +78,10 @@ def bbox_3D(labelmap, margin=2):
         hit = np.flatnonzero(labelmap.any(axis=tuple(a for a in range(labelmap.ndim) if a != ax)))
         out += [max(int(hit[0]) - margin, 0), min(int(hit[-1]) + margin + 1, labelmap.shape[ax])]
     return np.array(out)
+
+
+def get_DICOM_tags_to_keep():
+    """utils.get_DICOM_tags_to_keep (utils.py:407-414) lists the tags the reference copies from the input series into the
+    output image.  This build never copies DICOM tags (lungmask_b200/io.py: what `--removemetadata` asks for is always the
+    case), so the list is empty."""
+    return np.array([], dtype=str)
