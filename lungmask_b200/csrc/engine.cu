@@ -603,6 +603,8 @@ int lm_device(const lm_engine* e) { return e ? e->device : -1; }
 int lm_batch_capacity(const lm_engine* e) { return e ? e->B : 0; }
 size_t lm_weight_blob_floats(int n_classes) { return blob_floats(n_classes); }
 
+static int create_resources(lm_engine* e);
+
 int lm_create(int device, int batch_capacity, lm_engine** out) {
   if (!out) return fail(-1, "lm_create: out is NULL");
   *out = nullptr;
@@ -620,6 +622,20 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   e->device = device;
   e->B = batch_capacity;
   e->num_sms = prop.multiProcessorCount;
+  const int rc = create_resources(e);
+  if (rc) {  // nothing of a half-built engine survives a failed create (the message of the failing call is kept)
+    const std::string msg = g_err;
+    lm_destroy(e);
+    cudaGetLastError();
+    g_err = msg;
+    return rc;
+  }
+  *out = e;
+  return 0;
+}
+
+static int create_resources(lm_engine* e) {
+  const int batch_capacity = e->B;
   if (const char* c = getenv("LM_CHUNK_KB")) { int v = atoi(c); if (v >= 1) e->chunk_kb = e->chunk_kb_wide = v; }
   if (const char* c = getenv("LM_DUAL_ISSUE")) e->dual_issue = atoi(c) != 0;
   if (const char* c = getenv("LM_CTA_PAIRS")) e->cta_pairs = atoi(c) != 0;
@@ -647,7 +663,6 @@ int lm_create(int device, int batch_capacity, lm_engine** out) {
   CU(cudaMallocHost(&e->h_range, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int)));
   memset(e->h_range, 0, LM_MAX_SLOTS * RANGE_STRIDE * sizeof(int));
   RC(e->d_scratch.reserve(64));
-  *out = e;
   return 0;
 }
 
