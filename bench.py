@@ -172,7 +172,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = n * args.steps / dt
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": "CT slices/sec @256x256 (%s)" % args.config, "value": v, "unit": "slices/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": "CT slices/sec @256x256 (%s)" % ("R231" if args.config in ("C2", "C5") else args.config), "value": v, "unit": "slices/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["desc"], "config": args.config, "sample": "first %d slices of the volume per step" % n},
