@@ -42,9 +42,9 @@ STEM_GFLOP = 0.0755
 CONFIGS = {
     # K: classes of the (base) model; fill: classes of the fill model (fusion); S: slices per volume; vols: volumes per GPU and step
     "C2": dict(K=3, fill=None, S=300, batch=20, vols=1, gflop=96.20,
-               desc="R231 (3-class) 300-slice 256x256 int16 synthetic CT volume per GPU, batch_size=20 (engine waves of 37 slices)"),
+               desc="R231 (3-class) 300-slice 256x256 int16 synthetic CT volume per GPU, batch_size=20 (engine waves of %d slices)"),
     "C3": dict(K=6, fill=None, S=512, batch=32, vols=1, gflop=96.23,
-               desc="LTRCLobes (6-class) 512-slice 256x256 int16 synthetic CT volume per GPU, batch_size=32 (engine waves of 37 slices)"),
+               desc="LTRCLobes (6-class) 512-slice 256x256 int16 synthetic CT volume per GPU, batch_size=32 (engine waves of %d slices)"),
     "C4": dict(K=6, fill=3, S=300, batch=20, vols=1, gflop=96.23 + 96.20,
                desc="LTRCLobes_R231 fusion (6-class base + 3-class fill model, spare-label fusion, post-processing at original "
                     "resolution) on a 300-slice 256x256 int16 synthetic CT volume per GPU"),
@@ -175,7 +175,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "CT slices/sec @256x256 (%s)" % ("R231" if args.config in ("C2", "C5") else args.config), "value": v, "unit": "slices/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["desc"], "config": args.config, "sample": "first %d slices of the volume per step" % n},
+            "config": {"workload": cfg["desc"].replace("%d", "37"), "config": args.config, "sample": "first %d slices of the volume per step" % n},
             "cpu_baseline": {"value": v, "unit": "slices/s", "cores": cores, "kind": "port",
                              "sample": "%d slices per step (oracle port of mask.py:141-232 on host cores)" % n},
             "e2e": {"value": v, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -349,9 +349,9 @@ def run_engine(args):
             "dtype": "f16x3 (fp32-class: every fp32 value is an fp16 hi + scaled fp16 lo pair, 3 exact products per MAC, fp32 accumulate)",
             "data": "synthetic",
             "dice": parity["dice"], "label_flips": parity.get("label_flips"),
-            "config": {"workload": cfg["desc"], "config": args.config, "mode": args.mode, "volumes_per_step_per_gpu": nv,
+            "config": {"workload": cfg["desc"].replace("%d", str(inferer.wave_slices)), "config": args.config, "mode": args.mode, "volumes_per_step_per_gpu": nv,
                        "slices_per_step": slices_per_step,
-                       "l2": "inputs larger than L2: %d MB volume, ~6 GB of activations per 37-slice wave" % (vols[0].nbytes >> 20),
+                       "l2": "inputs larger than L2: %d MB volume, ~%d GB of activations per %d-slice wave" % (vols[0].nbytes >> 20, round(0.16 * inferer.wave_slices), inferer.wave_slices),
                        "weights": "seeded synthetic state_dict, 60 Adam steps on phantoms (released .pth needs network)",
                        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
                        "engine_env_options": {k: os.environ[k] for k in sorted(os.environ) if k.startswith("LM_") and k != "LM_TEST_EXPERIMENTAL"},

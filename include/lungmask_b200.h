@@ -174,7 +174,7 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * "stem_v2" (0 = first stem kernel, 1 = register-resident, 2 = shared-memory tile, the default),
  * "graphs" (1, default: a volume's forward - every wave's ~26 launches - is captured once as a CUDA graph and replayed;
  * 0: every kernel is launched individually; per-launch convolution timing and score taps always launch individually),
- * "upsample_v2" (0/1: cell-centred bilinear upsample kernel),
+ * "upsample_v2" (0: one thread per output sample, 1: per cell, 2 = default: per cell with static corner indexing; all bit-identical),
  * "merge_ctas" (0, default: the region merge loop of utils.py:310-339 runs on one CTA per SM in batches of independent
  * candidates; 1: the single-CTA sequential loop; n: that many CTAs),
  * "ccl_rule" (1 = pruned neighbour rule of the 26-connected labelling, the default; 0 = probe all 13 backward

@@ -205,7 +205,8 @@ struct lm_engine {
                           //    so far (r02: 14.3 vs 8.7 ms per 37-slice wave, profiles/r02_*) - opt-in
   int stem_v2 = 2;        // stem kernel version: 0 stem_kernel, 1 stem_kernel_v2 - weights in registers, 4-pixel quads
                           // (bit-identical to stem_kernel, r02 GPU tests), 2 (default) stem_kernel_v3 - shared input tile and weights
-  int upsample_v2 = 1;    // 1 (default): upsample2x_cells_kernel - one load per output sample (bit-identical to upsample2x_kernel)
+  int upsample_v2 = 2;    // 2 (default): upsample2x_cells_kernel<true> - one load per output sample, corners indexed statically;
+                          // 1: the same with run-time corner selection, 0: upsample2x_kernel (all three bit-identical)
   int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
   int chunk_kb_wide = 2;  // ... for the layers with Cout >= 128 (ring of 2 slots: chunk 1 leaves the tensor pipe waiting
                           // for the drain; chunk 2 costs < 1e-5 of score accuracy there, tools/debug_gpu.py)
@@ -284,7 +285,8 @@ int forward_batch(lm_engine* e, Slot& s, const void* d_in, bool in_f32, int n, u
     e->launches++;
     if (up < 4 && UPS[up].after_layer == i) {
       const ActSpec& src = ACT[UPS[up].src];
-      RC((e->upsample_v2 ? launch_upsample2x_cells : launch_upsample2x)(static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n,
+      RC((e->upsample_v2 >= 2 ? launch_upsample2x_cells_static : e->upsample_v2 ? launch_upsample2x_cells : launch_upsample2x)(
+          static_cast<const float*>(e->act[UPS[up].src]), e->act[UPS[up].dst], n,
                                                                       R >> src.level, R >> src.level, src.C, range + UPS[up].dst,
                                                                       s.act_scale[UPS[up].dst], e->num_sms, e->st));
       e->launches++;
@@ -643,7 +645,7 @@ static int create_resources(lm_engine* e) {
   if (const char* c = getenv("LM_GRAPHS")) e->use_graphs = atoi(c) != 0;
   if (const char* c = getenv("LM_BN64_MASK")) e->bn64_mask = (unsigned)strtoul(c, nullptr, 0);
   if (const char* c = getenv("LM_STEM_V2")) { const int v = atoi(c); e->stem_v2 = v < 0 ? 0 : (v > 2 ? 2 : v); }
-  if (const char* c = getenv("LM_UPSAMPLE_V2")) e->upsample_v2 = atoi(c) != 0;
+  if (const char* c = getenv("LM_UPSAMPLE_V2")) { const int v = atoi(c); e->upsample_v2 = v < 0 ? 0 : (v > 2 ? 2 : v); }
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
   if (const char* c = getenv("LM_MERGE_CTAS")) e->post.merge_ctas = atoi(c) > 0 ? atoi(c) : 0;
   if (const char* c = getenv("LM_CHUNK_KB_WIDE")) { int v = atoi(c); if (v >= 1) e->chunk_kb_wide = v; }
@@ -1249,7 +1251,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
   if (!strcmp(key, "weight_mcast")) { if (value != 0 && value != 2) return fail(-1, "weight_mcast must be 0 or 2"); e->weight_mcast = value; return 0; }
   if (!strcmp(key, "stem_v2")) { if (value < 0 || value > 2) return fail(-1, "stem_v2 must be 0, 1 or 2"); e->stem_v2 = value; return 0; }
-  if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value != 0; return 0; }
+  if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
   if (!strcmp(key, "shard_slab_ccl")) { e->shard_slab_ccl = value != 0; return 0; }
   if (!strcmp(key, "shard_test_slabs")) { if (value < 0 || value > kShardMaxWorld) return fail(-1, "shard_test_slabs out of range"); e->shard_test_slabs = value; return 0; }

@@ -315,7 +315,14 @@ __device__ __forceinline__ void up_axis(int o, int n_in, int& i0, int& i1, float
   l1 = s - (float)i0;
   l0 = 1.f - l1;
 }
-__global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __restrict__ in, op_t* __restrict__ out,
+// kStatic (default): for every output row the pair (i0, i1) that up_axis() names IS the pair of rows (ya, yb) the row's cell
+// loads - frame cells included: row 0 names (0, 1), row 2h-1 names (h-1, h-1) - and likewise per column
+// (tests/test_host_logic.py::test_upsample_cell_corners_are_the_rows_the_formula_names), so the corners are indexed
+// statically.  The run-time selection of the first version (kStatic = false, kept for the bit-identity test) put the 32
+// corner values into local memory (32 LDL + 8 STL per cell in the SASS) and hid from the compiler that the two samples of
+// a cell column share bilerp()'s `top` / `bot` terms: 921 -> 712 SASS instructions per cell, in an issue-bound kernel.
+template <bool kStatic>
+__global__ void __launch_bounds__(256, kStatic ? 3 : 0) upsample2x_cells_kernel(const float* __restrict__ in, op_t* __restrict__ out,
                                                                int N, int h, int w, int C, int* __restrict__ range_flag, float out_scale) {
   const int cq_per_pix = C / CPT;
   const int cw = w + 1, ch = h + 1;
@@ -348,27 +355,62 @@ __global__ void __launch_bounds__(256) upsample2x_cells_kernel(const float* __re
       p[1][0][4 * q] = c.x; p[1][0][4 * q + 1] = c.y; p[1][0][4 * q + 2] = c.z; p[1][0][4 * q + 3] = c.w;
       p[1][1][4 * q] = e.x; p[1][1][4 * q + 1] = e.y; p[1][1][4 * q + 2] = e.z; p[1][1][4 * q + 3] = e.w;
     }
+    if constexpr (kStatic) {
+      float ly[2][2], lx[2][2];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int y = 2 * ci + 1 + dy;
-      if (y < 0 || y >= H) continue;
-      int y0, y1; float ly0, ly1;
-      up_axis(y, h, y0, y1, ly0, ly1);
-      const int ry0 = (y0 == ya) ? 0 : 1, ry1 = (y1 == ya) ? 0 : 1;   // which of the two loaded rows (ya <= yb)
+      for (int d = 0; d < 2; ++d) {
+        int i0, i1;
+        up_axis(2 * ci + 1 + d, h, i0, i1, ly[d][0], ly[d][1]);
+        up_axis(2 * cj + 1 + d, w, i0, i1, lx[d][0], lx[d][1]);
+      }
+      float top[2][CPT], bot[2][CPT];   // bilerp()'s first two lines per cell column: shared by the column's two samples
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int x = 2 * cj + 1 + dx;
-        if (x < 0 || x >= W) continue;
-        int x0, x1; float lx0, lx1;
-        up_axis(x, w, x0, x1, lx0, lx1);
-        const int rx0 = (x0 == xa) ? 0 : 1, rx1 = (x1 == xa) ? 0 : 1;
-        float vv[CPT];
+      for (int e = 0; e < CPT; ++e) {
 #pragma unroll
-        for (int e = 0; e < CPT; ++e)
-          vv[e] = __fmul_rn(bilerp(p[ry0][rx0][e], p[ry0][rx1][e], p[ry1][rx0][e], p[ry1][rx1][e], lx0, lx1, ly0, ly1), out_scale);
-        const size_t r = (size_t)y * W + x;
-        op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
-        split_store(vv, o, o + oplane * C, ovf);
+        for (int dx = 0; dx < 2; ++dx) {
+          top[dx][e] = __fmaf_rn(lx[dx][1], p[0][1][e], __fmul_rn(lx[dx][0], p[0][0][e]));
+          bot[dx][e] = __fmaf_rn(lx[dx][1], p[1][1][e], __fmul_rn(lx[dx][0], p[1][0][e]));
+        }
+      }
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = 2 * ci + 1 + dy;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int x = 2 * cj + 1 + dx;
+          if (x < 0 || x >= W) continue;
+          float vv[CPT];
+#pragma unroll
+          for (int e = 0; e < CPT; ++e) vv[e] = __fmul_rn(__fmaf_rn(ly[dy][1], bot[dx][e], __fmul_rn(ly[dy][0], top[dx][e])), out_scale);
+          const size_t r = (size_t)y * W + x;
+          op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
+          split_store(vv, o, o + oplane * C, ovf);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = 2 * ci + 1 + dy;
+        if (y < 0 || y >= H) continue;
+        int y0, y1; float ly0, ly1;
+        up_axis(y, h, y0, y1, ly0, ly1);
+        const int ry0 = (y0 == ya) ? 0 : 1, ry1 = (y1 == ya) ? 0 : 1;   // which of the two loaded rows (ya <= yb)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int x = 2 * cj + 1 + dx;
+          if (x < 0 || x >= W) continue;
+          int x0, x1; float lx0, lx1;
+          up_axis(x, w, x0, x1, lx0, lx1);
+          const int rx0 = (x0 == xa) ? 0 : 1, rx1 = (x1 == xa) ? 0 : 1;
+          float vv[CPT];
+#pragma unroll
+          for (int e = 0; e < CPT; ++e)
+            vv[e] = __fmul_rn(bilerp(p[ry0][rx0][e], p[ry0][rx1][e], p[ry1][rx0][e], p[ry1][rx1][e], lx0, lx1, ly0, ly1), out_scale);
+          const size_t r = (size_t)y * W + x;
+          op_t* o = out + ((size_t)n * 2 * oplane + r) * C + cq * CPT;
+          split_store(vv, o, o + oplane * C, ovf);
+        }
       }
     }
   }
@@ -452,7 +494,14 @@ int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, in
 int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
                             cudaStream_t stream) {
   const size_t total = (size_t)N * (h + 1) * (w + 1) * (C / CPT);
-  upsample2x_cells_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag, out_scale);
+  upsample2x_cells_kernel<false><<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag, out_scale);
+  return (int)cudaGetLastError();
+}
+
+int launch_upsample2x_cells_static(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
+                                   cudaStream_t stream) {
+  const size_t total = (size_t)N * (h + 1) * (w + 1) * (C / CPT);
+  upsample2x_cells_kernel<true><<<grid_for(total, 256, num_sms), 256, 0, stream>>>(in, static_cast<op_t*>(out), N, h, w, C, range_flag, out_scale);
   return (int)cudaGetLastError();
 }
 

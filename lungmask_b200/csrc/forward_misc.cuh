@@ -25,6 +25,8 @@ int launch_upsample2x(const float* in, void* out, int N, int h, int w, int C, in
 // same samples, one thread per cell between four input pixels (1 load per output instead of 4); see forward_misc.cu
 int launch_upsample2x_cells(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
                             cudaStream_t stream);
+int launch_upsample2x_cells_static(const float* in, void* out, int N, int h, int w, int C, int* range_flag, float out_scale, int num_sms,
+                            cudaStream_t stream);
 // OIHW fp32 -> [2][taps][Cout][Cin] hi/lo operand planes
 int launch_prep_conv_weights(const float* oihw, void* out, int Cout, int Cin, int taps, int* range_flag, float w_scale,
                              cudaStream_t stream);

@@ -158,6 +158,8 @@ class LMInferer:
         self.model = get_model(self.modelname, modelpath)
         if wave_slices is None:
             wave_slices = 37 if batch_size >= 20 else batch_size
+            if batch_size >= 20 and os.environ.get("LM_WAVE_SLICES"):   # measurement hook: 74 = eight CTA rounds per level
+                wave_slices = max(1, min(1024, int(os.environ["LM_WAVE_SLICES"])))
         self.wave_slices = wave_slices
         self.engine = _native.Engine(device=device, batch_capacity=wave_slices)
         self.engine.load_weights(0, self.model.blob, self.model.n_classes)

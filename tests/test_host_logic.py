@@ -198,3 +198,20 @@ def test_lungmask_alias_package_resolves_to_engine_mirror():
     m = np.zeros((10, 10, 10), dtype=np.uint8)
     m[2:8, 3:7, 4:6] = 1
     assert tuple(bbox_3D(m, margin=2)) == (0, 10, 1, 9, 2, 8)
+
+
+def test_upsample_cell_corners_are_the_rows_the_formula_names():
+    """forward_misc.cu upsample2x_cells_kernel<true> indexes the four loaded corners statically.  That is exact iff, for every
+    output row y of a 2x bilinear upsample (align_corners=False, PyTorch's formula), the pair (i0, i1) the formula names
+    equals the pair (ya, yb) the cell containing y loads - frame cells included (the same holds per column)."""
+    f32 = np.float32
+    for h in range(1, 40):
+        for y in range(2 * h):
+            s = max(f32(0.5) * (f32(y) + f32(0.5)) - f32(0.5), f32(0.0))        # up_axis()
+            i0 = int(s)
+            i1 = i0 + (1 if i0 < h - 1 else 0)
+            ci = -1 if y == 0 else (y - 1) // 2                                   # the cell rows are 2 ci + 1 and 2 ci + 2
+            assert y - (2 * ci + 1) in (0, 1) and -1 <= ci <= h - 1
+            ya = 0 if ci < 0 else ci
+            yb = ya + 1 if ya + 1 < h else h - 1
+            assert (i0, i1) == (ya, yb), (h, y)
