@@ -257,98 +257,6 @@ __global__ void __launch_bounds__(256) stem_kernel_v3(const IT* __restrict__ in,
   if (ovf && range_flag) *range_flag = 1;
 }
 
-// stem_kernel_v4 (default since call 12 of round 2).  ncu of v3 (profiles/r02_call11_small_kernels.md): 0.46 of the HBM
-// write rate at 24 % occupancy and 56 % issue utilisation - 119 registers (a 4-pixel quad of 8 channels in flight per
-// thread) leave two blocks per SM, too few warps to cover the store and shared-memory latencies.  Same tile, same tables,
-// same arithmetic in the same order; a thread walks its two quads as four PIXEL PAIRS (16 accumulators), reads the
-// epilogue constants from shared memory when it needs them, and the kernel is compiled for four blocks per SM (64 registers).
-template <typename IT>
-__global__ void __launch_bounds__(256, 4) stem_kernel_v4(const IT* __restrict__ in, op_t* __restrict__ out,
-                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                         const float* __restrict__ scale, const float* __restrict__ shift,
-                                                         int N, int H, int W, int* __restrict__ range_flag, float out_scale) {
-  static_assert(CPT == 8, "stem_kernel_v4 is written for 8 channels per thread (fp16 operand planes)");
-  __shared__ float lut[1625];
-  __shared__ __align__(16) float sw[8][9][8];                 // [channel group][tap][channel within the group]
-  __shared__ __align__(16) float sc[8][3][8];                 // bias / scale / shift per channel group
-  __shared__ __align__(16) float tile[S3_TH + 2][S3_PITCH];
-  for (int i = threadIdx.x; i < 1625; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 1624.f);
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) { const int c = i / 9, tap = i % 9; sw[c >> 3][tap][c & 7] = w[i]; }
-  if (threadIdx.x < 64) {
-    const int c = threadIdx.x;
-    sc[c >> 3][0][c & 7] = bias[c]; sc[c >> 3][1][c & 7] = scale[c]; sc[c >> 3][2][c & 7] = shift[c];
-  }
-  const int tiles_x = W / S3_TW, tiles_y = H / S3_TH;
-  const int tiles_img = tiles_x * tiles_y;
-  const size_t plane = (size_t)H * W;
-  const int cq = threadIdx.x & 7;            // channel group
-  const int slot = threadIdx.x >> 3;         // 32 quad slots; the tile has 8 rows x 8 quads = 64 quads: two per slot
-  bool ovf = false;
-  for (int tile_id = blockIdx.x; tile_id < N * tiles_img; tile_id += gridDim.x) {
-    const int n = tile_id / tiles_img, r = tile_id - n * tiles_img;
-    const int y0 = (r / tiles_x) * S3_TH, x0 = (r % tiles_x) * S3_TW;
-    const IT* img = in + (size_t)n * plane;
-    __syncthreads();                         // the previous tile has been consumed (and, first time, the tables are ready)
-    for (int i = threadIdx.x; i < (S3_TH + 2) * (S3_TW + 2); i += blockDim.x) {
-      const int ty = i / (S3_TW + 2), tx = i - ty * (S3_TW + 2);
-      const int yy = y0 + ty - 1, xx = x0 + tx - 1;
-      float val = 0.f;                       // zero padding of the convolution
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = stem_input(img, (size_t)yy * W + xx, lut);
-      tile[ty][tx] = val;
-    }
-    __syncthreads();
-    op_t* const out_img = out + (size_t)n * 2 * plane * 64 + cq * 8;
-#pragma unroll 1
-    for (int pp = 0; pp < 4; ++pp) {
-      const int q = slot + 32 * (pp >> 1);   // quad index in the tile: row q / 8, columns 4 * (q % 8) ..; pair pp & 1 of it
-      const int ty = q >> 3, tx = (q & 7) * 4 + 2 * (pp & 1);
-      int cqv = cq;
-      asm volatile("" : "+r"(cqv));          // opaque per iteration: keeps the compiler from hoisting the 9 x 8 weights and the
-                                             // 24 epilogue constants out of the pair loop (72 + 24 registers: 119 in v3)
-      float win[3][4];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const float2 a = *reinterpret_cast<const float2*>(&tile[ty + dy][tx]), b = *reinterpret_cast<const float2*>(&tile[ty + dy][tx + 2]);
-        win[dy][0] = a.x; win[dy][1] = a.y; win[dy][2] = b.x; win[dy][3] = b.y;
-      }
-      float acc[2][8];
-#pragma unroll
-      for (int px = 0; px < 2; ++px)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[px][e] = 0.f;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float4 w0 = *reinterpret_cast<const float4*>(&sw[cqv][tap][0]), w1 = *reinterpret_cast<const float4*>(&sw[cqv][tap][4]);
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int px = 0; px < 2; ++px) {
-          const float v = win[tap / 3][px + tap % 3];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[px][e] = fmaf(wv[e], v, acc[px][e]);
-        }
-      }
-      const uint32_t rpix = (uint32_t)(y0 + ty) * (uint32_t)W + (uint32_t)(x0 + tx);
-#pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        float yv[8];
-#pragma unroll
-        for (int hq = 0; hq < 2; ++hq) {
-          const float4 b4 = *reinterpret_cast<const float4*>(&sc[cqv][0][4 * hq]);
-          const float4 s4 = *reinterpret_cast<const float4*>(&sc[cqv][1][4 * hq]);
-          const float4 h4 = *reinterpret_cast<const float4*>(&sc[cqv][2][4 * hq]);
-          yv[4 * hq + 0] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(acc[px][4 * hq + 0] + b4.x, 0.f), s4.x), h4.x), out_scale);
-          yv[4 * hq + 1] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(acc[px][4 * hq + 1] + b4.y, 0.f), s4.y), h4.y), out_scale);
-          yv[4 * hq + 2] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(acc[px][4 * hq + 2] + b4.z, 0.f), s4.z), h4.z), out_scale);
-          yv[4 * hq + 3] = __fmul_rn(__fadd_rn(__fmul_rn(fmaxf(acc[px][4 * hq + 3] + b4.w, 0.f), s4.w), h4.w), out_scale);
-        }
-        op_t* o = out_img + (size_t)(rpix + px) * 64;
-        split_store(yv, o, o + plane * 64, ovf);
-      }
-    }
-  }
-  if (ovf && range_flag) *range_flag = 1;
-}
-
 // One bilinear sample with a fixed operation order (explicit fused multiply-adds: both upsample kernels round alike)
 __device__ __forceinline__ float bilerp(float p00, float p01, float p10, float p11, float lx0, float lx1, float ly0, float ly1) {
   const float top = __fmaf_rn(lx1, p01, __fmul_rn(lx0, p00));
@@ -540,12 +448,7 @@ template <typename IT>
 static int launch_stem_t(const IT* in, void* out, const float* w, const float* bias, const float* scale, const float* shift, int N,
                          int H, int W, int* range_flag, float out_scale, int v2, int num_sms, cudaStream_t stream) {
   constexpr int QW = 4;
-  if (v2 >= 3 && W % S3_TW == 0 && H % S3_TH == 0 && CPT == 8) {
-    const int tiles = N * (W / S3_TW) * (H / S3_TH);
-    const int cap = num_sms * 8;             // four resident blocks per SM, two tiles each before the tail
-    stem_kernel_v4<IT><<<tiles < cap ? tiles : cap, 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag,
-                                                                 out_scale);
-  } else if (v2 >= 2 && W % S3_TW == 0 && H % S3_TH == 0 && CPT == 8) {
+  if (v2 >= 2 && W % S3_TW == 0 && H % S3_TH == 0 && CPT == 8) {
     const int tiles = N * (W / S3_TW) * (H / S3_TH);
     const int cap = num_sms * 6;
     stem_kernel_v3<IT><<<tiles < cap ? tiles : cap, 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag,

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round 2, call 12: stem_kernel_v4 (pixel pairs, 64 registers, four blocks per SM) as the default - smoke, the GPU suite without
+# Round 2, call 12: stem_kernel_v4 (v3 in pixel pairs, 64 registers, four blocks per SM; commit 0fb7d46, removed after this
+# call: bit-identical but 0.256 ms per wave against 0.187 ms, profiles/r02_call12_stem_kernel.md) as the default - smoke, the GPU suite without
 # the two CPU-oracle-heavy full-size tests (3.3 of its 4.9 minutes; they ran on the call-11 tree and the stem variants are
 # compared bit for bit inside test_gpu_zz_experimental.py), bench C2 with v4 and with v3, ncu --set full of the stem kernels.
 cd "$(dirname "$0")/.."
