@@ -171,7 +171,8 @@ LM_API int lm_last_timings(const lm_engine* e, float* ms7, int64_t* kernel_launc
  * layers, 2 for the wide ones), "dual_issue" (0/1: a second MMA-issuing thread per CTA on alternate chunks;
  * default 0), "cta_pairs" (0/1: the cta_group::2 convolution kernel: validated, on par, default 0),
  * "weight_mcast" (0 / 2: clusters of two CTAs share every weight stage through TMA multicast),
- * "stem_v2" (0 = first stem kernel, 1 = register-resident, 2 = shared-memory tile, the default),
+ * "stem_v2" (0 = first stem kernel, 1 = register-resident, 2 = shared-memory tile, 3 = the same with the next tile's
+ * samples fetched one tile ahead, the default; all bit-identical),
  * "graphs" (1, default: a volume's forward - every wave's ~26 launches - is captured once as a CUDA graph and replayed;
  * 0: every kernel is launched individually; per-launch convolution timing and score taps always launch individually),
  * "upsample_v2" (0: one thread per output sample, 1: per cell, 2 = default: per cell with static corner indexing; all bit-identical),

@@ -203,8 +203,9 @@ struct lm_engine {
   int weight_mcast = 0;   // 2: clusters of two CTAs share each weight stage through TMA multicast (conv_tc.cu, MC = 2)
   int cta_pairs = 0;      // 1: the cta_group::2 kernel (conv_tc_pair.cu): bit-identical on hardware, but slower than one CTA per tile
                           //    so far (r02: 14.3 vs 8.7 ms per 37-slice wave, profiles/r02_*) - opt-in
-  int stem_v2 = 2;        // stem kernel version: 0 stem_kernel, 1 stem_kernel_v2 - weights in registers, 4-pixel quads
-                          // (bit-identical to stem_kernel, r02 GPU tests), 2 (default) stem_kernel_v3 - shared input tile and weights
+  int stem_v2 = 3;        // stem kernel version: 0 stem_kernel, 1 stem_kernel_v2 - weights in registers, 4-pixel quads
+                          // (bit-identical to stem_kernel, r02 GPU tests), 2 stem_kernel_v3 - shared input tile and weights,
+                          // 3 (default) stem_kernel_v3 with the next tile's samples fetched one tile ahead
   int upsample_v2 = 2;    // 2 (default): upsample2x_cells_kernel<true> - one load per output sample, corners indexed statically;
                           // 1: the same with run-time corner selection, 0: upsample2x_kernel (all three bit-identical)
   int chunk_kb = 1;       // k-blocks per TMEM chunk for the 64-channel layers (ring of 4 slots)
@@ -644,7 +645,7 @@ static int create_resources(lm_engine* e) {
   if (const char* c = getenv("LM_WEIGHT_MCAST")) e->weight_mcast = atoi(c);
   if (const char* c = getenv("LM_GRAPHS")) e->use_graphs = atoi(c) != 0;
   if (const char* c = getenv("LM_BN64_MASK")) e->bn64_mask = (unsigned)strtoul(c, nullptr, 0);
-  if (const char* c = getenv("LM_STEM_V2")) { const int v = atoi(c); e->stem_v2 = v < 0 ? 0 : (v > 2 ? 2 : v); }
+  if (const char* c = getenv("LM_STEM_V2")) { const int v = atoi(c); e->stem_v2 = v < 0 ? 0 : (v > 3 ? 3 : v); }
   if (const char* c = getenv("LM_UPSAMPLE_V2")) { const int v = atoi(c); e->upsample_v2 = v < 0 ? 0 : (v > 2 ? 2 : v); }
   if (const char* c = getenv("LM_CCL_RULE")) e->post.ccl_rule = atoi(c) != 0;
   if (const char* c = getenv("LM_MERGE_CTAS")) e->post.merge_ctas = atoi(c) > 0 ? atoi(c) : 0;
@@ -1250,7 +1251,7 @@ int lm_set_option(lm_engine* e, const char* key, int value) {
   if (!strcmp(key, "dual_issue")) { e->dual_issue = value != 0; return 0; }
   if (!strcmp(key, "cta_pairs")) { e->cta_pairs = value != 0; return 0; }
   if (!strcmp(key, "weight_mcast")) { if (value != 0 && value != 2) return fail(-1, "weight_mcast must be 0 or 2"); e->weight_mcast = value; return 0; }
-  if (!strcmp(key, "stem_v2")) { if (value < 0 || value > 2) return fail(-1, "stem_v2 must be 0, 1 or 2"); e->stem_v2 = value; return 0; }
+  if (!strcmp(key, "stem_v2")) { if (value < 0 || value > 3) return fail(-1, "stem_v2 must be 0, 1, 2 or 3"); e->stem_v2 = value; return 0; }
   if (!strcmp(key, "upsample_v2")) { e->upsample_v2 = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
   if (!strcmp(key, "ccl_rule")) { e->post.ccl_rule = value != 0; return 0; }
   if (!strcmp(key, "shard_slab_ccl")) { e->shard_slab_ccl = value != 0; return 0; }

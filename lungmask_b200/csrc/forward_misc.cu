@@ -48,6 +48,15 @@ __device__ __forceinline__ float stem_input(const int16_t* img, size_t idx, cons
   return i >= 0 ? lut[i] : __fdiv_rn((float)i, 1624.f);
 }
 __device__ __forceinline__ float stem_input(const float* img, size_t idx, const float*) { return img[idx]; }
+// the same conversion from a sample that is already in a register (stem_kernel_v3<IT, true> fetches a tile's raw samples
+// one tile ahead)
+__device__ __forceinline__ float stem_convert(int16_t raw, const float* lut) {
+  int hu = raw;
+  hu = hu > 600 ? 600 : hu;
+  const int i = hu + 1024;
+  return i >= 0 ? lut[i] : __fdiv_rn((float)i, 1624.f);
+}
+__device__ __forceinline__ float stem_convert(float raw, const float*) { return raw; }
 
 template <typename IT>
 __global__ void __launch_bounds__(256) stem_kernel(const IT* __restrict__ in, op_t* __restrict__ out,
@@ -174,7 +183,11 @@ __global__ void __launch_bounds__(128) stem_kernel_v2(const IT* __restrict__ in,
 // LDS.128 broadcasts: 18 per quad of 4 pixels), and a thread computes 8 channels of a 4-pixel quad from 18 window loads.
 // Same arithmetic in the same order as stem_kernel (fmaf over the taps 0..8 from zero, then ReLU, BN, scale).
 constexpr int S3_TH = 8, S3_TW = 32, S3_PITCH = S3_TW + 2 + 2;   // tile rows / columns, padded row pitch of the input tile
-template <typename IT>
+// kPrefetch (default since call 13): ncu's stall breakdown of the plain version is led by long-scoreboard (1.8 stalled warps per
+// issue: the tile's global loads in front of the barrier) and barrier (0.9) stalls at two blocks per SM; here every thread
+// fetches its (at most two) raw samples of the NEXT tile into registers before it computes the current one, so the loads
+// fly during the 2400 instructions of the compute phase and the fill phase is shared-memory work only.
+template <typename IT, bool kPrefetch>
 __global__ void __launch_bounds__(256) stem_kernel_v3(const IT* __restrict__ in, op_t* __restrict__ out,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
@@ -196,19 +209,51 @@ __global__ void __launch_bounds__(256) stem_kernel_v3(const IT* __restrict__ in,
   const int cq = threadIdx.x & 7;            // channel group
   const int slot = threadIdx.x >> 3;         // 32 quad slots; the tile has 8 rows x 8 quads = 64 quads: two per slot
   bool ovf = false;
+  constexpr int TILE_ELEMS = (S3_TH + 2) * (S3_TW + 2);   // 340 samples incl. the halo: at most two per thread
+  static_assert(TILE_ELEMS <= 2 * 256, "two samples per thread");
+  IT raw[2] = {IT(0), IT(0)};
+  bool ok[2] = {false, false};
+  auto fetch = [&](int tid_) {               // raw samples of tile tid_ -> registers (no conversion, nothing waited for)
+    const int n_ = tid_ / tiles_img, r_ = tid_ - n_ * tiles_img;
+    const int y0_ = (r_ / tiles_x) * S3_TH, x0_ = (r_ % tiles_x) * S3_TW;
+    const IT* img_ = in + (size_t)n_ * plane;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + 256 * k;
+      const int ty = i / (S3_TW + 2), tx = i - ty * (S3_TW + 2);
+      const int yy = y0_ + ty - 1, xx = x0_ + tx - 1;
+      ok[k] = i < TILE_ELEMS && yy >= 0 && yy < H && xx >= 0 && xx < W;
+      raw[k] = ok[k] ? img_[(size_t)yy * W + xx] : IT(0);
+    }
+  };
+  if (kPrefetch && (int)blockIdx.x < N * tiles_img) fetch(blockIdx.x);
   for (int tile_id = blockIdx.x; tile_id < N * tiles_img; tile_id += gridDim.x) {
     const int n = tile_id / tiles_img, r = tile_id - n * tiles_img;
     const int y0 = (r / tiles_x) * S3_TH, x0 = (r % tiles_x) * S3_TW;
     const IT* img = in + (size_t)n * plane;
     __syncthreads();                         // the previous tile has been consumed (and, first time, the tables are ready)
-    for (int i = threadIdx.x; i < (S3_TH + 2) * (S3_TW + 2); i += blockDim.x) {
-      const int ty = i / (S3_TW + 2), tx = i - ty * (S3_TW + 2);
-      const int yy = y0 + ty - 1, xx = x0 + tx - 1;
-      float val = 0.f;                       // zero padding of the convolution
-      if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = stem_input(img, (size_t)yy * W + xx, lut);
-      tile[ty][tx] = val;
+    if constexpr (kPrefetch) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        if (i < TILE_ELEMS) {
+          const int ty = i / (S3_TW + 2), tx = i - ty * (S3_TW + 2);
+          tile[ty][tx] = ok[k] ? stem_convert(raw[k], lut) : 0.f;   // 0: zero padding of the convolution
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < TILE_ELEMS; i += blockDim.x) {
+        const int ty = i / (S3_TW + 2), tx = i - ty * (S3_TW + 2);
+        const int yy = y0 + ty - 1, xx = x0 + tx - 1;
+        float val = 0.f;                       // zero padding of the convolution
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = stem_input(img, (size_t)yy * W + xx, lut);
+        tile[ty][tx] = val;
+      }
     }
     __syncthreads();
+    if constexpr (kPrefetch) {
+      if (tile_id + (int)gridDim.x < N * tiles_img) fetch(tile_id + gridDim.x);
+    }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int q = slot + 32 * half;        // quad index in the tile: row q / 8, columns 4 * (q % 8) ..
@@ -451,8 +496,12 @@ static int launch_stem_t(const IT* in, void* out, const float* w, const float* b
   if (v2 >= 2 && W % S3_TW == 0 && H % S3_TH == 0 && CPT == 8) {
     const int tiles = N * (W / S3_TW) * (H / S3_TH);
     const int cap = num_sms * 6;
-    stem_kernel_v3<IT><<<tiles < cap ? tiles : cap, 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W, range_flag,
-                                                                 out_scale);
+    if (v2 >= 3)
+      stem_kernel_v3<IT, true><<<tiles < cap ? tiles : cap, 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W,
+                                                                         range_flag, out_scale);
+    else
+      stem_kernel_v3<IT, false><<<tiles < cap ? tiles : cap, 256, 0, stream>>>(in, static_cast<op_t*>(out), w, bias, scale, shift, N, H, W,
+                                                                          range_flag, out_scale);
   } else if (v2 && W % QW == 0) {
     const size_t threads = (size_t)N * H * (W / QW) * (64 / CPT);
     size_t blocks = (threads + 127) / 128;

@@ -12,7 +12,7 @@ from oracle import restate, synth
 pytestmark = pytest.mark.gpu   # validated on hardware in round 2: always run
 
 
-DEFAULTS = {"stem_v2": 2, "upsample_v2": 2, "cta_pairs": 0, "weight_mcast": 0}
+DEFAULTS = {"stem_v2": 3, "upsample_v2": 2, "cta_pairs": 0, "weight_mcast": 0}
 
 
 def _forward(engine, resized, **options):
@@ -36,7 +36,7 @@ def setup(engine):
     return resized, _forward(engine, resized)
 
 
-@pytest.mark.parametrize("option,value", [("stem_v2", 0), ("stem_v2", 1), ("upsample_v2", 0), ("upsample_v2", 1), ("cta_pairs", 1), ("weight_mcast", 2)])
+@pytest.mark.parametrize("option,value", [("stem_v2", 0), ("stem_v2", 1), ("stem_v2", 2), ("upsample_v2", 0), ("upsample_v2", 1), ("cta_pairs", 1), ("weight_mcast", 2)])
 def test_experimental_kernel_is_bit_identical(engine, setup, option, value):
     """every alternative kernel against the default configuration"""
     resized, (labels, scores) = setup
