@@ -78,3 +78,28 @@ def test_forward_and_apply_equal_reference(ref, tmp_path):
     x = torch.as_tensor(restate.normalise(taps["resized"])[:, None], dtype=torch.float32)
     with torch.inference_mode():
         assert torch.equal(inf.model(x), torch.as_tensor(taps["scores"]))
+
+
+def test_preprocess_equals_reference_on_ragged_and_noisy_volumes(ref):
+    """slices smaller than the 128 x 128 thumbnail, non-square and odd sizes, volumes without a clear body"""
+    shapes = [(2, 17, 23), (1, 128, 128), (2, 129, 127), (1, 64, 300), (2, 511, 513), (1, 33, 33), (2, 200, 100), (1, 12, 12),
+              (2, 256, 255), (1, 150, 400)]
+    vols = [synth.phantom(*sh, seed=50 + i) for i, sh in enumerate(shapes)]
+    rng = np.random.default_rng(0)
+    vols += [rng.normal(-400, 400, size=(2, 90 + 7 * i, 110 + 5 * i)).astype(np.int16) for i in range(6)]
+    for vol in vols:
+        a, ba = ref.utils.preprocess(vol, resolution=[256, 256])
+        r, br = restate.preprocess(vol, resolution=[256, 256])
+        assert np.array_equal(a, r) and np.array_equal(np.asarray(ba), np.asarray(br)), vol.shape
+
+
+def test_postprocessing_equals_reference_sweep(ref):
+    """random sizes, class counts and speckle levels x the spare / skip_below combinations of utils.py:272"""
+    rng = np.random.default_rng(0)
+    for seed in range(10, 22):
+        S, K = int(rng.integers(1, 7)), int(rng.choice([3, 6]))
+        lab = synth.label_noise_volume(S, K, seed=seed, speckle=float(rng.choice([5e-4, 2e-3, 1e-2])), H=int(rng.choice([48, 64, 96])),
+                                       W=int(rng.choice([48, 80, 128])))
+        for spare, skip in (([], 3), ([K - 1], 3), ([], 1), ([1], 2)):
+            a = ref.utils.postprocessing(lab.copy(), spare=list(spare), disable_tqdm=True, skip_below=skip)
+            assert np.array_equal(a, restate.postprocessing(lab.copy(), spare=list(spare), skip_below=skip)), (seed, S, K, spare, skip)
